@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    config.addinivalue_line("markers", "needs_reference: needs /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    have_gpu = torch.cuda.is_available()
+    have_ref = os.path.isdir("/root/reference/SeqRec")
+    for item in items:
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "needs_reference" in item.keywords and not have_ref:
+            item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
