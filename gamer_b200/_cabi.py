@@ -1,0 +1,98 @@
+"""ctypes binding of libgamer_b200.so — signatures are derived from include/gamer_b200.h so they cannot drift.
+
+The product path fails loudly when the library is missing: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), "include", "gamer_b200.h")
+LIB_PATH = os.path.join(HERE, "lib", "libgamer_b200.so")
+
+_CTYPES = {
+    "int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float,
+    "gamer_stream_t": ctypes.c_void_p,
+}
+
+
+def parse_header(path: str = HEADER) -> dict:
+    """{name: (restype, [(argtype, argname), ...])} for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    decls = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(gamer_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if "typedef" in ret:
+            continue
+        parsed = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                mm = re.match(r"(.*?)(\w+)$", a)
+                parsed.append((mm.group(1).strip(), mm.group(2)))
+        decls[name] = (ret, parsed)
+    return decls
+
+
+def _to_ctype(t: str):
+    t = t.replace("const", "").strip()
+    if t.endswith("*"):
+        return ctypes.c_char_p if t.replace(" ", "") == "char*" else ctypes.c_void_p
+    return _CTYPES[t]
+
+
+class _Lib:
+    def __init__(self):
+        self._lib = None
+        self.decls = parse_header()
+
+    def load(self):
+        if self._lib is not None:
+            return self._lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"gamer_b200: native library {LIB_PATH} is missing — run `python -m gamer_b200.build` "
+                "(there is no CPU/PyTorch fallback for the hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (ret, args) in self.decls.items():
+            fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+            fn.restype = _to_ctype(ret)
+            fn.argtypes = [_to_ctype(t) for t, _ in args]
+        self._lib = lib
+        return lib
+
+
+_LIB = _Lib()
+
+
+def lib():
+    return _LIB.load()
+
+
+def declared_symbols():
+    return sorted(_LIB.decls)
+
+
+class GamerError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().gamer_last_error()
+        raise GamerError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def call(name: str, *args):
+    fn = getattr(lib(), name)
+    rc = fn(*args)
+    check(rc, name)

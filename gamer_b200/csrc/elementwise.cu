@@ -1,0 +1,216 @@
+// Small fused elementwise kernels around the GEMMs: SwiGLU, the cross-attention output gate, row gather into the
+// expert-permuted space, and the fused softmax-cross-entropy (loss + dlogits in one pass over the logits).
+//
+// Reference semantics: MyQwen3MoeMLP.forward  down(silu(gate x) * up x)  (SeqRec/models/generative/Qwen3Moe/FFN.py:25-27);
+// o_proj(a) * silu(gating(h)) (Qwen3Multi/model.py:146-147); ForCausalLMLoss (transformers loss_utils.py:28-68).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// gu: [R, 2*I] (gate | up), act: [R, I]
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, bf16* __restrict__ act, long long ld_act,
+                                  long long R, int I) {
+    const int vec_per_row = I / 8;
+    const long long total = R * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i % vec_per_row) * 8;
+        float g[8], u[8], o[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = g[k] * sigmoidf_(g[k]) * u[k];
+        *reinterpret_cast<bf16x8*>(act + r * ld_act + c) = float_to_bf16x8(o);
+    }
+}
+
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, const bf16* __restrict__ dact,
+                                  long long ld_dact, bf16* __restrict__ dgu, long long ld_dgu, long long R, int I) {
+    const int vec_per_row = I / 8;
+    const long long total = R * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i % vec_per_row) * 8;
+        float g[8], u[8], d[8], dg[8], du[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dact + r * ld_dact + c), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float s = sigmoidf_(g[k]);
+            du[k] = d[k] * g[k] * s;
+            dg[k] = d[k] * u[k] * s * (1.0f + g[k] * (1.0f - s));
+        }
+        *reinterpret_cast<bf16x8*>(dgu + r * ld_dgu + c) = float_to_bf16x8(dg);
+        *reinterpret_cast<bf16x8*>(dgu + r * ld_dgu + I + c) = float_to_bf16x8(du);
+    }
+}
+
+// out = x + y * silu(g)      (all [R, W]; g has its own row stride: it lives inside the fused projection buffer)
+__global__ void gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                         const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ out, long long R,
+                                         int W) {
+    const int vec_per_row = W / 8;
+    const long long total = R * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i % vec_per_row) * 8;
+        float xf[8], yf[8], gf[8], o[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + r * W + c), xf);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(g + r * ld_g + c), gf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = xf[k] + yf[k] * gf[k] * sigmoidf_(gf[k]);
+        *reinterpret_cast<bf16x8*>(out + r * W + c) = float_to_bf16x8(o);
+    }
+}
+
+// dy = dout * silu(g);  dg = dout * y * silu'(g)
+__global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y,
+                                         const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ dy,
+                                         bf16* __restrict__ dg, long long ld_dg, long long R, int W) {
+    const int vec_per_row = W / 8;
+    const long long total = R * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i % vec_per_row) * 8;
+        float d[8], yf[8], gf[8], o1[8], o2[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + r * W + c), d);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(g + r * ld_g + c), gf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float s = sigmoidf_(gf[k]);
+            o1[k] = d[k] * gf[k] * s;
+            o2[k] = d[k] * yf[k] * s * (1.0f + gf[k] * (1.0f - s));
+        }
+        *reinterpret_cast<bf16x8*>(dy + r * W + c) = float_to_bf16x8(o1);
+        *reinterpret_cast<bf16x8*>(dg + r * ld_dg + c) = float_to_bf16x8(o2);
+    }
+}
+
+// dst[r, :] = rows[r] >= 0 ? src[rows[r], :] : 0
+__global__ void gather_rows_kernel(const bf16* __restrict__ src, long long ld_src, const int* __restrict__ rows,
+                                   const int* __restrict__ n_rows_dev, long long n_rows_max, bf16* __restrict__ dst,
+                                   long long ld_dst, int W) {
+    const int vec_per_row = W / 8;
+    const long long n_rows = n_rows_dev ? min((long long)*n_rows_dev, n_rows_max) : n_rows_max;
+    const long long total = n_rows * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i % vec_per_row) * 8;
+        const int sr = rows[r];
+        bf16x8 v;
+        v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+        if (sr >= 0) v = *reinterpret_cast<const bf16x8*>(src + (long long)sr * ld_src + c);
+        *reinterpret_cast<bf16x8*>(dst + r * ld_dst + c) = v;
+    }
+}
+
+// fused softmax cross-entropy over fp32 logits rows: one warp per row.
+//   loss_row[r] = lse - logit[label] (0 when label == ignore);  dlogits[r, :] = (softmax - onehot) * scale (bf16; columns
+//   [V, ld_d) zero-filled so the buffer can feed TMA-tiled GEMMs).  scale = grad_scale * (*inv_norm).
+__global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long long* __restrict__ labels,
+                                  long long R, int V, int ignore_index, const float* __restrict__ inv_norm,
+                                  float grad_scale, float* __restrict__ loss_row, bf16* __restrict__ dlogits,
+                                  long long ld_d) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float scale = grad_scale * (inv_norm ? *inv_norm : 1.0f);
+    for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += (long long)gridDim.x * wpb) {
+        const float* lp = logits + r * ld_l;
+        const long long lab = labels[r];
+        const bool valid = lab != ignore_index;
+        float mx = -INFINITY;
+        for (int c = lane; c < V; c += 32) mx = fmaxf(mx, lp[c]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < V; c += 32) se += expf(lp[c] - mx);
+        se = warp_sum(se);
+        const float lse = mx + logf(se);
+        if (lane == 0) loss_row[r] = valid ? (lse - lp[lab]) : 0.f;
+        if (dlogits != nullptr) {
+            bf16* dp = dlogits + r * ld_d;
+            const float inv = valid ? scale / se : 0.f;
+            for (int c = lane; c < ld_d; c += 32) {
+                float v = 0.f;
+                if (c < V && valid) v = expf(lp[c] - mx) * inv - ((c == lab) ? scale : 0.f);
+                dp[c] = __float2bfloat16(v);
+            }
+        }
+    }
+}
+
+inline int grid_for(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+}
+
+}  // namespace
+
+extern "C" int gamer_swiglu_fwd(const void* gu, long long ld_gu, void* act, long long ld_act, long long R, int I,
+                                cudaStream_t stream) {
+    GAMER_REQUIRE(I % 8 == 0, "intermediate size must be a multiple of 8");
+    if (R == 0) return 0;
+    swiglu_fwd_kernel<<<grid_for(R * (I / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(gu), ld_gu,
+                                                                      reinterpret_cast<bf16*>(act), ld_act, R, I);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_swiglu_bwd(const void* gu, long long ld_gu, const void* dact, long long ld_dact, void* dgu,
+                                long long ld_dgu, long long R, int I, cudaStream_t stream) {
+    GAMER_REQUIRE(I % 8 == 0, "intermediate size must be a multiple of 8");
+    if (R == 0) return 0;
+    swiglu_bwd_kernel<<<grid_for(R * (I / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(gu), ld_gu, reinterpret_cast<const bf16*>(dact), ld_dact,
+        reinterpret_cast<bf16*>(dgu), ld_dgu, R, I);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_gate_residual_fwd(const void* x, const void* y, const void* g, long long ld_g, void* out,
+                                       long long R, int W, cudaStream_t stream) {
+    GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
+    if (R == 0) return 0;
+    gate_residual_fwd_kernel<<<grid_for(R * (W / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(g), ld_g,
+        reinterpret_cast<bf16*>(out), R, W);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_gate_residual_bwd(const void* dout, const void* y, const void* g, long long ld_g, void* dy,
+                                       void* dg, long long ld_dg, long long R, int W, cudaStream_t stream) {
+    GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
+    if (R == 0) return 0;
+    gate_residual_bwd_kernel<<<grid_for(R * (W / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(g), ld_g,
+        reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dg), ld_dg, R, W);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_gather_rows(const void* src, long long ld_src, const int* rows, const int* n_rows_dev,
+                                 long long n_rows_max, void* dst, long long ld_dst, int W, cudaStream_t stream) {
+    GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
+    if (n_rows_max == 0) return 0;
+    gather_rows_kernel<<<grid_for(n_rows_max * (W / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows_dev, n_rows_max, reinterpret_cast<bf16*>(dst), ld_dst, W);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_ce_fwd_bwd(const float* logits, long long ld_l, const long long* labels, long long R, int V,
+                                int ignore_index, const float* inv_norm, float grad_scale, float* loss_row,
+                                void* dlogits, long long ld_d, cudaStream_t stream) {
+    if (R == 0) return 0;
+    const int wpb = 8;
+    const int grid = (int)((R + wpb - 1) / wpb < 148 * 8 ? (R + wpb - 1) / wpb : 148 * 8);
+    ce_fwd_bwd_kernel<<<grid, wpb * 32, 0, stream>>>(logits, ld_l, labels, R, V, ignore_index, inv_norm, grad_scale,
+                                                     loss_row, reinterpret_cast<bf16*>(dlogits), ld_d);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}

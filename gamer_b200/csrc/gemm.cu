@@ -1,0 +1,567 @@
+// bf16 GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA, fp32 accumulation.
+//
+//   gemm_tn  : C[r, n] (+)= alpha * sum_k A[r, k] * B[g(r)*N + n, k]      (forward projections and dgrad)
+//              optional expert groups (row segments -> weight slab g), residual add, row scatter, fp32 out.
+//   wgrad    : dW[g][i, j] += sum_r dY[r, i] * X[r, j]                     (both operands MN-major in smem)
+//
+// One persistent CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  4-stage smem ring, 2 TMEM accumulator stages so the
+// epilogue of tile t overlaps the MMAs of tile t+1.
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_GROUPS = 8;
+
+struct GemmParams {
+    int rows;  // rows of A (upper bound in grouped mode)
+    int N, K;
+    int n_groups;
+    const int* seg_off;  // device int32[n_groups+1], 128-aligned segment starts; nullptr => one group
+    void* C;
+    long long ldc;
+    const bf16* resid;
+    long long ldr;
+    const int* row_map;  // out row for A-row r (-1: skip); nullptr => identity
+    float alpha;
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    using S = GemmSmem<BLOCK_N>;
+    constexpr int STAGES = S::STAGES;
+    constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512 (power of two)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // segment table -> registers
+    int seg[MAX_GROUPS + 1];
+    int row_end = p.rows;
+    if (p.seg_off != nullptr) {
+#pragma unroll
+        for (int g = 0; g <= MAX_GROUPS; ++g) seg[g] = (g <= p.n_groups) ? p.seg_off[g] : 0x7fffffff;
+        row_end = min(row_end, p.seg_off[p.n_groups]);
+    } else {
+        seg[0] = 0;
+#pragma unroll
+        for (int g = 1; g <= MAX_GROUPS; ++g) seg[g] = 0x7fffffff;
+    }
+    const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int m_tiles = (p.rows + BLOCK_M - 1) / BLOCK_M;
+    const int total = n_tiles * m_tiles;
+    const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    auto group_of = [&](int row0) {
+        int g = 0;
+#pragma unroll
+        for (int i = 1; i < MAX_GROUPS; ++i) g += (row0 >= seg[i]) ? 1 : 0;
+        return g;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+                const int row0 = m_blk * BLOCK_M;
+                if (row0 >= row_end) break;
+                const int g = group_of(row0);
+                const int brow = g * p.N + n_blk * BLOCK_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * S::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, row0);
+                    tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, brow);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int row0 = (t / n_tiles) * BLOCK_M;
+            if (row0 >= row_end) break;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ad = umma_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t bd = umma_desc_sw128(sb + k * UMMA_K * 2, 16, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+            const int row0 = m_blk * BLOCK_M;
+            if (row0 >= row_end) break;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = row0 + quarter * 32 + lane;
+            long long orow = -1;
+            if (row < row_end) orow = (p.row_map != nullptr) ? (long long)p.row_map[row] : (long long)row;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + c;
+                if (orow >= 0 && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                    const bool full = (col0 + 32 <= p.N);
+                    if (p.resid != nullptr) {
+                        const bf16* rp = p.resid + orow * p.ldr + col0;
+                        if (full) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                bf16x8 rv = *reinterpret_cast<const bf16x8*>(rp + 8 * q);
+                                float f[8];
+                                bf16x8_to_float(rv, f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[8 * q + i] += f[i];
+                            }
+                        } else {
+                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += __bfloat162float(rp[i]);
+                        }
+                    }
+                    if constexpr (OUT_F32) {
+                        float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + col0;
+                        if (full) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4*>(cp + 4 * q) =
+                                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        } else {
+                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = v[i];
+                        }
+                    } else {
+                        bf16* cp = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + col0;
+                        if (full) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) *reinterpret_cast<bf16x8*>(cp + 8 * q) = float_to_bf16x8(v + 8 * q);
+                        } else {
+                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = __float2bfloat16(v[i]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: dW[g][i, j] += sum_r dY[r, i] * X[r, j].  The reduction runs over token rows, which is the slow dimension
+// of both operands, so they are staged as MN-major SWIZZLE_128B tiles: TMA boxes of [64 rows x 64 cols] (128-byte
+// rows), UMMA descriptors with LBO = 8192 (next 64-wide MN atom = next box) and SBO = 1024 (next 8 k-rows).
+// Work item = (group, row chunk, i-block, j-block); partial sums are reduced with fp32 red.global.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int W_CHUNK_ROWS = 2048;
+constexpr int W_STAGES = 4;
+constexpr int W_BOX_BYTES = 64 * 64 * 2;           // 8 KB
+constexpr int W_A_BYTES = 2 * W_BOX_BYTES;         // 128 output rows (i)
+constexpr int W_B_BYTES = 4 * W_BOX_BYTES;         // up to 256 output cols (j)
+constexpr int W_STAGE_BYTES = W_A_BYTES + W_B_BYTES;
+constexpr int W_SMEM_TOTAL = W_STAGES * W_STAGE_BYTES + 1024 + 256;
+
+struct WgradParams {
+    int rows, N_out, K_in, n_groups;
+    const int* seg_off;
+    float* dW;
+    int bj;        // j-block width (multiple of 64, <= 256)
+    int n_i, n_j;  // output tile grid
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + W_STAGES * W_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + W_STAGES;
+    uint64_t* tfull_bar = empty_bar + W_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmY);
+        prefetch_tmap(&tmX);
+        for (int s = 0; s < W_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // chunk table: group g owns chunks [cstart[g], cstart[g+1])
+    int gbeg[MAX_GROUPS], gend[MAX_GROUPS], cstart[MAX_GROUPS + 1];
+    cstart[0] = 0;
+#pragma unroll
+    for (int g = 0; g < MAX_GROUPS; ++g) {
+        int b = 0, e = 0;
+        if (g < p.n_groups) {
+            if (p.seg_off != nullptr) {
+                b = p.seg_off[g];
+                e = min(p.seg_off[g + 1], p.rows);
+            } else {
+                b = 0;
+                e = p.rows;
+            }
+        }
+        gbeg[g] = b;
+        gend[g] = e;
+        cstart[g + 1] = cstart[g] + (max(e - b, 0) + W_CHUNK_ROWS - 1) / W_CHUNK_ROWS;
+    }
+    const int n_ij = p.n_i * p.n_j;
+    const int total = cstart[MAX_GROUPS] * n_ij;
+    const int n_jbox = p.bj / 64;
+    const uint32_t stage_tx = (uint32_t)(2 + n_jbox) * W_BOX_BYTES;
+
+    auto decode = [&](int w, int& g, int& r0, int& r1, int& ib, int& jb) {
+        const int chunk = w / n_ij, ij = w % n_ij;
+        ib = ij / p.n_j;
+        jb = ij % p.n_j;
+        g = 0;
+#pragma unroll
+        for (int i = 1; i < MAX_GROUPS; ++i) g += (chunk >= cstart[i]) ? 1 : 0;
+        r0 = 0;
+        r1 = 0;
+#pragma unroll
+        for (int i = 0; i < MAX_GROUPS; ++i)
+            if (i == g) {
+                r0 = gbeg[i] + (chunk - cstart[i]) * W_CHUNK_ROWS;
+                r1 = min(r0 + W_CHUNK_ROWS, gend[i]);
+            }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                int g, r0, r1, ib, jb;
+                decode(w, g, r0, r1, ib, jb);
+                for (int r = r0; r < r1; r += 64) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * W_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], stage_tx);
+                    tma_load_2d(sa, &tmY, &full_bar[stage], ib * 128, r);
+                    tma_load_2d(sa + W_BOX_BYTES, &tmY, &full_bar[stage], ib * 128 + 64, r);
+                    for (int c = 0; c < n_jbox; ++c)
+                        tma_load_2d(sa + W_A_BYTES + c * W_BOX_BYTES, &tmX, &full_bar[stage], jb * p.bj + c * 64, r);
+                    if (++stage == W_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_bf16(128, p.bj, 1, 1);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            int g, r0, r1, ib, jb;
+            decode(w, g, r0, r1, ib, jb);
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int r = r0; r < r1; r += 64) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * W_STAGE_BYTES);
+                    const uint32_t sb = sa + W_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // 4 x 16 token rows per 64-row stage
+                        const uint64_t ad = umma_desc_sw128(sa + k * 16 * 128, W_BOX_BYTES, 1024);
+                        const uint64_t bd = umma_desc_sw128(sb + k * 16 * 128, W_BOX_BYTES, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (r != r0 || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (r + 64 >= r1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == W_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            int g, r0, r1, ib, jb;
+            decode(w, g, r0, r1, ib, jb);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int i = ib * 128 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+            float* out = p.dW + ((long long)g * p.N_out + i) * p.K_in;
+            for (int c = 0; c < p.bj; c += 32) {
+                uint32_t rr[32];
+                tmem_ld_32x32(taddr + c, rr);
+                tmem_ld_wait();
+                const int j0 = jb * p.bj + c;
+                if (i < p.N_out) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (j0 + q < p.K_in) atomicAdd(out + j0 + q, __uint_as_float(rr[q]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plain CUDA-core reference GEMMs: GPU-side checkers for the tests (never on the product path)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ref_gemm_tn_kernel(const bf16* A, long long lda, const bf16* B, long long ldb, float* C, long long ldc,
+                                   int rows, int N, int K) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (n >= N || r >= rows) return;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += __bfloat162float(A[r * lda + k]) * __bfloat162float(B[n * ldb + k]);
+    C[r * ldc + n] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], SWIZZLE_128B.
+int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    GAMER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    GAMER_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    GAMER_REQUIRE((ld * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes (ld=%lld)", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
+                  cols, ld);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int BLOCK_N, bool OUT_F32>
+int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using S = GemmSmem<BLOCK_N>;
+    auto kern = gemm_tn_kernel<BLOCK_N, OUT_F32>;
+    static bool configured = false;
+    if (!configured) {
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const void* B, long long ldb, int n_groups,
+                                  int N, int K, const int* seg_off, void* C, long long ldc, int c_is_f32,
+                                  const void* resid, long long ldr, const int* row_map, float alpha,
+                                  cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    GAMER_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, "n_groups=%d out of range", n_groups);
+    GAMER_REQUIRE(n_groups == 1 || seg_off != nullptr, "grouped GEMM needs seg_off");
+    CUtensorMap tmA, tmB;
+    const int block_n = (N % 256 == 0) ? 256 : 128;
+    if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;
+    if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, block_n)) return e;
+    GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha};
+    if (block_n == 256)
+        return c_is_f32 ? launch_gemm_tn<256, true>(tmA, tmB, p, stream) : launch_gemm_tn<256, false>(tmA, tmB, p, stream);
+    return c_is_f32 ? launch_gemm_tn<128, true>(tmA, tmB, p, stream) : launch_gemm_tn<128, false>(tmA, tmB, p, stream);
+}
+
+extern "C" int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* X, long long ldx, int rows, int N_out,
+                                     int K_in, int n_groups, const int* seg_off, float* dW, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    GAMER_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, "n_groups=%d out of range", n_groups);
+    GAMER_REQUIRE(n_groups == 1 || seg_off != nullptr, "grouped wgrad needs seg_off");
+    CUtensorMap tmY, tmX;
+    if (int e = make_tmap_bf16(&tmY, dY, rows, N_out, ldy, 64)) return e;
+    if (int e = make_tmap_bf16(&tmX, X, rows, K_in, ldx, 64)) return e;
+    WgradParams p;
+    p.rows = rows;
+    p.N_out = N_out;
+    p.K_in = K_in;
+    p.n_groups = n_groups;
+    p.seg_off = seg_off;
+    p.dW = dW;
+    p.n_i = ceil_div(N_out, 128);
+    p.n_j = ceil_div(K_in, 256);
+    p.bj = ceil_div(ceil_div(K_in, p.n_j), 64) * 64;
+    static bool configured = false;
+    if (!configured) {
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_TOTAL));
+        configured = true;
+    }
+    // upper bound on work items (grouped: every group may add one partial chunk)
+    const long long items = (long long)(ceil_div(rows, W_CHUNK_ROWS) + n_groups) * p.n_i * p.n_j;
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    wgrad_kernel<<<grid, NUM_THREADS, W_SMEM_TOTAL, stream>>>(tmY, tmX, p);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+// GPU-side reference (tests only): C fp32 = A * B^T on CUDA cores
+extern "C" int gamer_ref_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc,
+                                 int rows, int N, int K, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    dim3 grid(ceil_div(N, 128), rows);
+    ref_gemm_tn_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(B),
+                                                 ldb, C, ldc, rows, N, K);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,398 @@
+// K2/K3: RMSNorm (hidden rows), and the per-head q/k RMSNorm + behaviour-embedding add + RoPE block.
+//
+// Reference semantics: Qwen3RMSNorm  w * (x * rsqrt(mean(x^2) + eps))  with fp32 statistics
+// (transformers modeling_qwen3_moe.py:290-308, used at SeqRec/models/generative/Qwen3Multi/model.py:50-51,165-176,284);
+// q/k/v behaviour embeddings added before the head norm (Qwen3Multi/model.py:88-95); half-split RoPE
+// (modeling_qwen3_moe.py:56-86) with cos/sin tables computed by the host exactly as Qwen3RotaryEmbedding does.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// rmsnorm over H = 256 columns: one warp per row, 8 columns (16 B) per lane.
+//   out row = row_map ? row_map[m] : m, row stride ld_out; optional 64-wide behaviour-embedding concat after col H.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int H256 = 256;
+
+__global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, float eps, long long M,
+                                   bf16* __restrict__ out, long long ld_out, const int* __restrict__ row_map,
+                                   const bf16* __restrict__ cat_table, const int* __restrict__ cat_idx, int cat_dim,
+                                   float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float wv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = w[lane * 8 + i];
+    for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8), f);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss * (1.0f / H256) + eps);
+        if (lane == 0 && rstd_out != nullptr) rstd_out[m] = rstd;
+        const long long orow = row_map ? (long long)row_map[m] : m;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = wv[i] * (f[i] * rstd);
+        bf16* op = out + orow * ld_out;
+        *reinterpret_cast<bf16x8*>(op + lane * 8) = float_to_bf16x8(f);
+        if (cat_table != nullptr && lane < cat_dim / 8) {
+            const bf16x8 e = *reinterpret_cast<const bf16x8*>(cat_table + (long long)cat_idx[m] * cat_dim + lane * 8);
+            *reinterpret_cast<bf16x8*>(op + H256 + lane * 8) = e;
+        }
+    }
+}
+
+// backward.  dh rows come from (row_map ? row_map[m] : m) with stride ld_dh.
+//   dx[m] = (dres ? dres[m] : 0) + rstd*g - x*rstd^3*mean(g.x),  g = w*dh
+//   dw   += sum_m dh*x*rstd        (block partials -> fp32 atomics)
+//   dcat[cat_idx[m]] += dh[m, H:H+cat_dim]
+__global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ rstd_in, float eps, long long M,
+                                   const bf16* __restrict__ dh, long long ld_dh, const int* __restrict__ row_map,
+                                   const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dw,
+                                   const int* __restrict__ cat_idx, int cat_dim, int cat_rows,
+                                   float* __restrict__ dcat) {
+    extern __shared__ float sh[];  // [H256] dw partials, then [cat_rows*cat_dim]
+    float* sdw = sh;
+    float* scat = sh + H256;
+    for (int i = threadIdx.x; i < H256 + cat_rows * cat_dim; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float wv[8], dwacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        wv[i] = w[lane * 8 + i];
+        dwacc[i] = 0.f;
+    }
+    for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
+        float xf[8], df[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8), xf);
+        const long long srow = row_map ? (long long)row_map[m] : m;
+        const bf16* dp = dh + srow * ld_dh;
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + lane * 8), df);
+        float rstd;
+        if (rstd_in != nullptr) {
+            rstd = rstd_in[m];
+        } else {
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss += xf[i] * xf[i];
+            rstd = rsqrtf(warp_sum(ss) * (1.0f / H256) + eps);
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dwacc[i] += df[i] * xf[i] * rstd;
+            df[i] *= wv[i];
+            dot += df[i] * xf[i];
+        }
+        dot = warp_sum(dot) * (1.0f / H256) * rstd * rstd * rstd;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * df[i] - xf[i] * dot;
+        if (dres != nullptr) {
+            float rf[8];
+            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dres + m * H256 + lane * 8), rf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += rf[i];
+        }
+        *reinterpret_cast<bf16x8*>(dx + m * H256 + lane * 8) = float_to_bf16x8(o);
+        if (dcat != nullptr && lane < cat_dim / 8) {
+            float cf[8];
+            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + H256 + lane * 8), cf);
+            const int r = cat_idx[m];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&scat[r * cat_dim + lane * 8 + i], cf[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sdw[lane * 8 + i], dwacc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < H256; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+    if (dcat != nullptr)
+        for (int i = threadIdx.x; i < cat_rows * cat_dim; i += blockDim.x)
+            if (scat[i] != 0.f) atomicAdd(&dcat[i], scat[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-head block on the fused projection buffer [M, ld]: columns [0,384) q (6 heads), [384,576) k (3), [576,768) v (3).
+// 8 lanes per 64-wide head (16 B each): lanes j<4 hold the first half, j>=4 the second (RoPE partner = lane ^ 4).
+//   q,k: u = raw (+ emb[act]);  n = wn * u * rsqrt(mean(u^2)+eps);  out = n*cos + rotate_half(n)*sin
+//   v  : out = raw (+ emb[act])
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HD = 64;
+
+struct HeadArgs {
+    long long M;
+    int L;                 // tokens per sequence (position = m % L when pos_ids == nullptr)
+    int n_q, n_kv;
+    const int* pos_ids;    // [M] RoPE positions or nullptr
+    int pos0;              // added to m % L when pos_ids == nullptr (decode steps)
+    const float* cos_tab;  // [n_pos, 32]
+    const float* sin_tab;
+    const float* qn_w;     // [64]
+    const float* kn_w;
+    const bf16* q_emb;     // [n_beh+1, n_q*64] or nullptr (self attention)
+    const bf16* k_emb;
+    const bf16* v_emb;
+    const int* act_idx;    // [M]
+    float eps;
+};
+
+__global__ void qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw,
+                                        bf16* __restrict__ out, long long ld_out) {
+    const int n_heads = a.n_q + 2 * a.n_kv;
+    const int sub = threadIdx.x & 7;           // lane within the head group
+    const long long groups = a.M * n_heads;
+    const long long gid0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long gstride = ((long long)gridDim.x * blockDim.x) >> 3;
+    // uniform trip count: the 4 head groups of a warp may be q, k or v heads, so every shuffle below is executed by
+    // all 32 lanes and results are selected afterwards
+    const long long iters = (groups + gstride - 1) / gstride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long gidx = gid0 + it * gstride;
+        const bool live = gidx < groups;
+        const long long m = live ? gidx / n_heads : 0;
+        const int h = live ? (int)(gidx % n_heads) : 0;
+        const int col = h * HD + sub * 8;
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(raw + m * ld_raw + col), f);
+        const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
+        const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
+        if (emb != nullptr) {
+            const int width = is_q ? a.n_q * HD : a.n_kv * HD;
+            const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
+            float e[8];
+            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(emb + (long long)a.act_idx[m] * width + hc), e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += e[i];
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
+        const float* wn = is_q ? a.qn_w : a.kn_w;
+        const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
+        const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
+        const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float n = wn[sub * 8 + i] * (f[i] * rstd);
+            const float partner = __shfl_xor_sync(0xffffffffu, n, 4);
+            o[i] = n * ct[i] + ((sub < 4) ? -partner : partner) * st[i];
+        }
+        if (is_q || is_k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = o[i];
+        }
+        if (live) *reinterpret_cast<bf16x8*>(out + m * ld_out + col) = float_to_bf16x8(f);
+    }
+}
+
+// backward: d_out (grad wrt rotated q,k and v) -> d_raw; accumulates d qn_w / d kn_w and the behaviour-embedding grads.
+__global__ void qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw,
+                                        const bf16* __restrict__ dout, long long ld_dout, bf16* __restrict__ draw,
+                                        long long ld_draw, float* __restrict__ d_qn_w, float* __restrict__ d_kn_w,
+                                        float* __restrict__ d_q_emb, float* __restrict__ d_k_emb,
+                                        float* __restrict__ d_v_emb, int emb_rows) {
+    extern __shared__ float sh[];  // [2*64] norm-weight grads | [emb_rows * (n_q + 2 n_kv) * 64] embedding grads
+    const int n_heads = a.n_q + 2 * a.n_kv;
+    const int emb_w = n_heads * HD;
+    float* sdw = sh;
+    float* semb = sh + 2 * HD;
+    const bool has_emb = d_q_emb != nullptr;
+    for (int i = threadIdx.x; i < 2 * HD + (has_emb ? emb_rows * emb_w : 0); i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const long long groups = a.M * n_heads;
+    const long long gid0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long gstride = ((long long)gridDim.x * blockDim.x) >> 3;
+    // trip count padded so that all 8 lanes of a group (and all groups of a warp) stay convergent for the shuffles
+    const long long iters = (groups + gstride - 1) / gstride;
+    float dwq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // this lane's 8 norm-weight columns
+    for (long long it = 0; it < iters; ++it) {
+        const long long gidx = gid0 + it * gstride;
+        const bool live = gidx < groups;
+        const long long m = live ? gidx / n_heads : 0;
+        const int h = live ? (int)(gidx % n_heads) : 0;
+        const int col = h * HD + sub * 8;
+        const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
+        float u[8], d[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(raw + m * ld_raw + col), u);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + m * ld_dout + col), d);
+        const int act = (has_emb && live) ? a.act_idx[m] : 0;
+        if (has_emb) {
+            const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
+            const int width = is_q ? a.n_q * HD : a.n_kv * HD;
+            const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
+            float e[8];
+            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(emb + (long long)act * width + hc), e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] += e[i];
+        }
+        float du[8];
+        {
+            const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
+            const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
+            const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
+            const float* wn = is_q ? a.qn_w : a.kn_w;
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss += u[i] * u[i];
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
+            float dn[8], dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float partner = __shfl_xor_sync(0xffffffffu, d[i], 4);
+                // transpose of the rotation: first half gets +sin * d[second], second half gets -sin * d[first]
+                dn[i] = d[i] * ct[i] + ((sub < 4) ? partner : -partner) * st[i];
+                const float g = wn[sub * 8 + i] * dn[i];
+                dot += g * u[i];
+                du[i] = g;
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            dot *= (1.0f / HD) * rstd * rstd * rstd;
+            if (is_q || is_k) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float gw = live ? dn[i] * u[i] * rstd : 0.f;
+                    dwq[i] += is_q ? gw : 0.f;
+                    dwk[i] += is_q ? 0.f : gw;
+                    du[i] = rstd * du[i] - u[i] * dot;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) du[i] = d[i];
+            }
+        }
+        if (live) {
+            *reinterpret_cast<bf16x8*>(draw + m * ld_draw + col) = float_to_bf16x8(du);
+            if (has_emb) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(&semb[act * emb_w + col + i], du[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sdw[sub * 8 + i], dwq[i]);
+        atomicAdd(&sdw[HD + sub * 8 + i], dwk[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HD; i += blockDim.x) {
+        if (sdw[i] != 0.f) atomicAdd(&d_qn_w[i], sdw[i]);
+        if (sdw[HD + i] != 0.f) atomicAdd(&d_kn_w[i], sdw[HD + i]);
+    }
+    if (has_emb) {
+        const int qw = a.n_q * HD, kw = a.n_kv * HD;
+        for (int i = threadIdx.x; i < emb_rows * emb_w; i += blockDim.x) {
+            const float v = semb[i];
+            if (v == 0.f) continue;
+            const int r = i / emb_w, c = i % emb_w;
+            if (c < qw) atomicAdd(&d_q_emb[r * qw + c], v);
+            else if (c < qw + kw) atomicAdd(&d_k_emb[r * kw + (c - qw)], v);
+            else atomicAdd(&d_v_emb[r * kw + (c - qw - kw)], v);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gamer_rmsnorm_fwd(const void* x, const float* w, float eps, long long M, int H, void* out,
+                                 long long ld_out, const int* row_map, const void* cat_table, const int* cat_idx,
+                                 int cat_dim, float* rstd, cudaStream_t stream) {
+    GAMER_REQUIRE(H == H256, "rmsnorm kernels are specialised for hidden size 256 (got %d)", H);
+    GAMER_REQUIRE(cat_dim % 8 == 0 && cat_dim <= 256, "cat_dim must be a multiple of 8 and <= 256");
+    if (M == 0) return 0;
+    const int wpb = 8;
+    const int grid = (int)((M + wpb - 1) / wpb < 148 * 8 ? (M + wpb - 1) / wpb : 148 * 8);
+    rmsnorm_fwd_kernel<<<grid, wpb * 32, 0, stream>>>(reinterpret_cast<const bf16*>(x), w, eps, M,
+                                                      reinterpret_cast<bf16*>(out), ld_out, row_map,
+                                                      reinterpret_cast<const bf16*>(cat_table), cat_idx, cat_dim, rstd);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_rmsnorm_bwd(const void* x, const float* w, const float* rstd, float eps, long long M, int H,
+                                 const void* dh, long long ld_dh, const int* row_map, const void* dres, void* dx,
+                                 float* dw, const int* cat_idx, int cat_dim, int cat_rows, float* dcat,
+                                 cudaStream_t stream) {
+    GAMER_REQUIRE(H == H256, "rmsnorm kernels are specialised for hidden size 256 (got %d)", H);
+    if (M == 0) return 0;
+    const int wpb = 8;
+    const int grid = (int)((M + wpb - 1) / wpb < 148 * 4 ? (M + wpb - 1) / wpb : 148 * 4);
+    const int cr = dcat ? cat_rows : 0;
+    const size_t smem = (H256 + cr * cat_dim) * sizeof(float);
+    rmsnorm_bwd_kernel<<<grid, wpb * 32, smem, stream>>>(
+        reinterpret_cast<const bf16*>(x), w, rstd, eps, M, reinterpret_cast<const bf16*>(dh), ld_dh, row_map,
+        reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dw, cat_idx, cat_dim, cr, dcat);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+static HeadArgs make_head_args(long long M, int L, int n_q, int n_kv, const int* pos_ids, int pos0,
+                               const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
+                               const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx, float eps) {
+    HeadArgs a;
+    a.M = M; a.L = L; a.n_q = n_q; a.n_kv = n_kv; a.pos_ids = pos_ids; a.pos0 = pos0;
+    a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.qn_w = qn_w; a.kn_w = kn_w;
+    a.q_emb = reinterpret_cast<const bf16*>(q_emb); a.k_emb = reinterpret_cast<const bf16*>(k_emb);
+    a.v_emb = reinterpret_cast<const bf16*>(v_emb); a.act_idx = act_idx; a.eps = eps;
+    return a;
+}
+
+extern "C" int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* out, long long ld_out, long long M, int L,
+                                      int n_q, int n_kv, int head_dim, const int* pos_ids, int pos0,
+                                      const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
+                                      const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx,
+                                      float eps, cudaStream_t stream) {
+    GAMER_REQUIRE(head_dim == HD, "head kernels are specialised for head_dim 64 (got %d)", head_dim);
+    if (M == 0) return 0;
+    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
+                                act_idx, eps);
+    const long long groups = M * (n_q + 2 * n_kv);
+    const long long blocks = (groups * 8 + 255) / 256;
+    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    qk_norm_rope_fwd_kernel<<<grid, 256, 0, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
+                                                      reinterpret_cast<bf16*>(out), ld_out);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const void* dout, long long ld_dout, void* draw,
+                                      long long ld_draw, long long M, int L, int n_q, int n_kv, int head_dim,
+                                      const int* pos_ids, int pos0, const float* cos_tab, const float* sin_tab,
+                                      const float* qn_w, const float* kn_w, const void* q_emb, const void* k_emb,
+                                      const void* v_emb, const int* act_idx, int emb_rows, float eps, float* d_qn_w,
+                                      float* d_kn_w, float* d_q_emb, float* d_k_emb, float* d_v_emb,
+                                      cudaStream_t stream) {
+    GAMER_REQUIRE(head_dim == HD, "head kernels are specialised for head_dim 64 (got %d)", head_dim);
+    if (M == 0) return 0;
+    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
+                                act_idx, eps);
+    const bool has_emb = q_emb != nullptr;
+    GAMER_REQUIRE(!has_emb || (d_q_emb && d_k_emb && d_v_emb), "behaviour-embedding grads missing");
+    const size_t smem = (2 * HD + (has_emb ? emb_rows * (n_q + 2 * n_kv) * HD : 0)) * sizeof(float);
+    GAMER_REQUIRE(smem <= 48 * 1024, "too many behaviour rows for the shared-memory accumulator");
+    const long long groups = M * (n_q + 2 * n_kv);
+    const long long blocks = (groups * 8 + 255) / 256;
+    const int grid = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
+    qk_norm_rope_bwd_kernel<<<grid, 256, smem, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
+                                                         reinterpret_cast<const bf16*>(dout), ld_dout,
+                                                         reinterpret_cast<bf16*>(draw), ld_draw, d_qn_w, d_kn_w,
+                                                         has_emb ? d_q_emb : nullptr, d_k_emb, d_v_emb, emb_rows);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}

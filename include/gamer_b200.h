@@ -1,0 +1,121 @@
+/* gamer_b200 — C-ABI of the B200-native GAMER decoder hot path.
+ *
+ * The reference (wzf2000/GAMER) is pure Python/PyTorch and has no FFI of its own; the boundary its hot path sits
+ * behind is the HF-model Python surface.  This header is the native boundary underneath that
+ * surface: every entry point replaces the stock PyTorch/library kernels executed by the reference call site cited
+ * next to it (paths relative to the reference's SeqRec/ package).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw pointers, sizes and a cudaStream_t; no torch types.  All data pointers are DEVICE pointers owned
+ *     by the caller; nothing is allocated inside (workspace sizes come from the *_bytes helpers).
+ *   - every call is asynchronous on `stream`; return 0 = ok, negative = error, message via gamer_last_error()
+ *     (thread-local).  One host thread per device.
+ *   - activations are bf16 (uint16 storage), statistics / gradients of parameters fp32, indices int32 unless noted.
+ *   - "ld" arguments are row strides in ELEMENTS.
+ */
+#ifndef GAMER_B200_H
+#define GAMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gamer_stream_t; /* == cudaStream_t */
+
+#define GAMER_MASK_CAUSAL 0        /* Qwen3Multi self:   j<=i & am[j]                     Qwen3Multi/model.py:691-741 */
+#define GAMER_MASK_MULTI_CROSS 1   /* Qwen3Multi cross:  j<=i & act[j]<act[i] & am[j]      Qwen3Multi/model.py:573-630 */
+#define GAMER_MASK_SESSION 2       /* Session* self:     (item(j)==item(i)&j<=i | s[j]<s[i]) & am[j]
+                                                                                        Qwen3SessionMoe/model.py:416-468 */
+#define GAMER_MASK_SESSION_CROSS 3 /* SessionMulti cross: s[j]<s[i] & act[j]<act[i] & am[j]
+                                                                                     Qwen3SessionMulti/model.py:556-613 */
+
+const char* gamer_last_error(void);
+
+/* ---- K1: embedding gather + router indices ------------------------------------------------------------------
+ * replaces embed_tokens(input_ids) (Qwen3Multi/model.py:779) and Qwen3MultiDecoderRouter.forward
+ * (Qwen3Multi/router.py:74-201; Qwen3Moe/router.py:74-154).  ids/ctx are int64 as the reference passes them.
+ * Token s of row b sits at absolute position pos0+s; ctx (may be NULL = ids) is the whole sequence so far. */
+int gamer_embed_route_fwd(const long long* ids, const long long* ctx, long long ctx_ld, int B, int S, int pos0,
+                          int tokens_per_item, int pad, int eos, int vocab, const int* beh_lut, int n_beh,
+                          const void* table_bf16, int H, void* x_bf16, int* pos_idx, int* beh_idx, int* act_idx,
+                          gamer_stream_t stream);
+/* expert routing permutation for MyQwen3SparseMLP (Qwen3Moe/FFN.py:53-72): expert = position index. */
+long long gamer_route_perm_workspace_bytes(int B);
+int gamer_route_perm_build(const int* pos_idx, int B, int S, int n_experts, void* workspace, int* perm, int* rows,
+                           long long rows_capacity, int* seg_off, gamer_stream_t stream);
+/* sparse embedding gradient (embedding_dense_backward of nn.Embedding(padding_idx=4), Qwen3Multi/model.py:263). */
+long long gamer_embed_sort_bytes(long long M, int vocab);
+int gamer_embed_sort_build(const long long* ids, long long M, int vocab, int pad, void* sort_buf, gamer_stream_t stream);
+int gamer_embed_bwd(const void* dx_bf16, long long M, int H, int vocab, const void* sort_buf, float* dtable,
+                    gamer_stream_t stream);
+
+/* ---- K2/K3: RMSNorm, head norm + behaviour embedding + RoPE ---------------------------------------------------
+ * Qwen3RMSNorm (Qwen3Multi/model.py:165-176,205,222,239,284,869); q/k norm, behaviour embeddings and
+ * apply_rotary_pos_emb (Qwen3Multi/model.py:88-101); FFN behaviour-embedding concat (Qwen3Moe/FFN.py:60-62). */
+int gamer_rmsnorm_fwd(const void* x, const float* w, float eps, long long M, int H, void* out, long long ld_out,
+                      const int* row_map, const void* cat_table, const int* cat_idx, int cat_dim, float* rstd,
+                      gamer_stream_t stream);
+int gamer_rmsnorm_bwd(const void* x, const float* w, const float* rstd, float eps, long long M, int H, const void* dh,
+                      long long ld_dh, const int* row_map, const void* dres, void* dx, float* dw, const int* cat_idx,
+                      int cat_dim, int cat_rows, float* dcat, gamer_stream_t stream);
+int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* out, long long ld_out, long long M, int L, int n_q,
+                           int n_kv, int head_dim, const int* pos_ids, int pos0, const float* cos_tab,
+                           const float* sin_tab, const float* qn_w, const float* kn_w, const void* q_emb,
+                           const void* k_emb, const void* v_emb, const int* act_idx, float eps, gamer_stream_t stream);
+int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const void* dout, long long ld_dout, void* draw,
+                           long long ld_draw, long long M, int L, int n_q, int n_kv, int head_dim, const int* pos_ids,
+                           int pos0, const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
+                           const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx, int emb_rows,
+                           float eps, float* d_qn_w, float* d_kn_w, float* d_q_emb, float* d_k_emb, float* d_v_emb,
+                           gamer_stream_t stream);
+
+/* ---- K4/K7: tcgen05 GEMMs ------------------------------------------------------------------------------------
+ * q/k/v/o/gating nn.Linear (Qwen3Multi/model.py:38-49,66,93-99,147-149), expert gate/up/down projections
+ * (Qwen3Moe/FFN.py:19-27,64-68) and lm_head (Qwen3Multi/model.py:1001).
+ *   C[r, n] = alpha * sum_k A[r,k] * B[g(r)*N + n, k]  (+ resid[out_row, n]);  out_row = row_map ? row_map[r] : r
+ * grouped mode: seg_off[n_groups+1] (device) gives 128-aligned row segments, segment g uses weight slab g. */
+int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const void* B, long long ldb, int n_groups, int N, int K,
+                       const int* seg_off, void* C, long long ldc, int c_is_f32, const void* resid, long long ldr,
+                       const int* row_map, float alpha, gamer_stream_t stream);
+/* dW[g][i, j] += sum_r dY[r, i] * X[r, j]   (fp32 accumulate into dW [n_groups, N_out, K_in]) */
+int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* X, long long ldx, int rows, int N_out, int K_in,
+                          int n_groups, const int* seg_off, float* dW, gamer_stream_t stream);
+/* CUDA-core checker used by the GPU tests only */
+int gamer_ref_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int rows,
+                      int N, int K, gamer_stream_t stream);
+
+/* ---- K6: masked attention (replaces mask materialisation + SDPA, Qwen3Multi/model.py:123-143,573-741) ---------- */
+long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv);
+int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
+                   int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
+                   float scale, void* workspace, void* o, long long ld_o, float* lse, gamer_stream_t stream);
+long long gamer_attn_bwd_workspace_bytes(int B, int L, int n_q);
+int gamer_attn_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
+                   int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
+                   float scale, const void* o, const void* d_o, long long ld_o, const float* lse, void* workspace,
+                   void* dq, void* dk, void* dv, long long ld_d, gamer_stream_t stream);
+
+/* ---- elementwise pieces --------------------------------------------------------------------------------------- */
+int gamer_swiglu_fwd(const void* gu, long long ld_gu, void* act, long long ld_act, long long R, int I,
+                     gamer_stream_t stream);
+int gamer_swiglu_bwd(const void* gu, long long ld_gu, const void* dact, long long ld_dact, void* dgu, long long ld_dgu,
+                     long long R, int I, gamer_stream_t stream);
+int gamer_gate_residual_fwd(const void* x, const void* y, const void* g, long long ld_g, void* out, long long R, int W,
+                            gamer_stream_t stream);
+int gamer_gate_residual_bwd(const void* dout, const void* y, const void* g, long long ld_g, void* dy, void* dg,
+                            long long ld_dg, long long R, int W, gamer_stream_t stream);
+int gamer_gather_rows(const void* src, long long ld_src, const int* rows, const int* n_rows_dev, long long n_rows_max,
+                      void* dst, long long ld_dst, int W, gamer_stream_t stream);
+
+/* ---- K8: fused softmax cross-entropy (ForCausalLMLoss, Qwen3Multi/model.py:904-922) ---------------------------- */
+int gamer_ce_fwd_bwd(const float* logits, long long ld_l, const long long* labels, long long R, int V, int ignore_index,
+                     const float* inv_norm, float grad_scale, float* loss_row, void* dlogits, long long ld_d,
+                     gamer_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMER_B200_H */
