@@ -514,6 +514,10 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
     if (rows <= 0) return 0;
     GAMER_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, "n_groups=%d out of range", n_groups);
     GAMER_REQUIRE(n_groups == 1 || seg_off != nullptr, "grouped GEMM needs seg_off");
+    GAMER_REQUIRE(ldc % (c_is_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  "C rows must be 16-byte aligned (ldc=%lld)", ldc);
+    GAMER_REQUIRE(resid == nullptr || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0),
+                  "residual rows must be 16-byte aligned (ldr=%lld)", ldr);
     CUtensorMap tmA, tmB;
     const int block_n = (N % 256 == 0) ? 256 : 128;
     if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;

@@ -33,13 +33,19 @@ def test_gemm_tn_plain(rows, N, K):
     torch.manual_seed(0)
     a = bf(torch.randn(rows, K, device=DEV))
     b = bf(torch.randn(N, K, device=DEV) * 0.1)
-    out = k.gemm_tn(a, b, N)
+    ldc = (N + 63) // 64 * 64          # output rows must stay 16-byte aligned (N = 1041 -> 1088-wide buffer)
+    out = torch.empty(rows, ldc, dtype=torch.bfloat16, device=DEV)
+    k.gemm_tn(a, b, N, out=out)
     ref = a.float() @ b.float().t()
-    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+    assert rel_err(out[:, :N], ref) < 6e-3, rel_err(out[:, :N], ref)
     chk = k.ref_gemm_tn(a, b, N, K)
     assert rel_err(chk, ref) < 1e-5
-    out32 = k.gemm_tn(a, b, N, out_f32=True, alpha=0.5)
-    assert rel_err(out32, 0.5 * ref) < 1e-5, rel_err(out32, 0.5 * ref)
+    out32 = torch.empty(rows, ldc, dtype=torch.float32, device=DEV)
+    k.gemm_tn(a, b, N, out=out32, alpha=0.5)
+    assert rel_err(out32[:, :N], 0.5 * ref) < 1e-5, rel_err(out32[:, :N], 0.5 * ref)
+    if ldc != N:
+        with pytest.raises(Exception, match="16-byte aligned"):
+            k.gemm_tn(a, b, N)
 
 
 def test_gemm_tn_k_tail_and_stride():
@@ -103,7 +109,8 @@ def test_gemm_tn_grouped_scatter_residual():
 def test_gemm_wgrad_plain(rows, N_out, K_in):
     k = _k()
     torch.manual_seed(3)
-    dy = bf(torch.randn(rows, N_out, device=DEV) * 0.1)
+    ld = (N_out + 63) // 64 * 64
+    dy = bf(torch.randn(rows, ld, device=DEV) * 0.1)[:, :N_out]
     x = bf(torch.randn(rows, K_in, device=DEV))
     dw = torch.zeros(1, N_out, K_in, device=DEV)
     k.gemm_wgrad(dy, x, N_out, K_in, dw)

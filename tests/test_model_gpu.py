@@ -1,0 +1,134 @@
+"""GPU: the drop-in model classes (CUDA path through the C-ABI) against the golden vectors frozen from the reference
+and against the fp32 oracle on the same seeded inputs and weights.
+
+Tolerances (bf16 activations / fp32 accumulation vs the reference's fp32 recipe):
+  logits  : relative Frobenius error <= 2e-2 and max |diff| <= 2e-2 * max|logit| + 2e-2
+  loss    : |diff| <= 5e-3 * max(1, |loss|)
+  grads   : per-parameter norm within 3e-2 relative; sampled entries cosine >= 0.999 where the golden holds >= 32
+            non-zero samples; rel-L2 <= 3e-2 for the full embedding gradient
+  router indices: bit-exact.
+"""
+import pytest
+import torch
+
+from tests.helpers import load_golden, spec_from_golden, weights_from_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CLASSES = {"Qwen3Multi": "Qwen3MultiWithTemperature", "Qwen3SessionMoe": "Qwen3SessionMoeWithTemperature",
+           "Qwen3SessionMulti": "Qwen3SessionMultiWithTemperature"}
+
+
+def build_model(g, temperature=None):
+    from transformers.models.qwen3_moe import Qwen3MoeConfig
+    from gamer_b200 import modeling
+    c = dict(g["config"])
+    cfg = Qwen3MoeConfig(**{k: v for k, v in c.items() if k != "rope_theta"})
+    cfg.rope_theta = c["rope_theta"]
+    cfg.mlp_type = "Qwen3"
+    cfg.Moe_behavior_only = False
+    cfg.tie_word_embeddings = True
+    cfg.use_behavior_token = True
+    cfg.use_user_token = False
+    m = getattr(modeling, CLASSES[g["variant"]])(cfg)
+    sd = weights_from_golden(g)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k == "lm_head.weight" for k in missing)
+    m.tie_weights()
+    m.set_hyper(temperature if temperature is not None else g.get("temperature", 1.0))
+    return m.to(DEV)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+TRAIN = ["train_qwen3multi.pt", "train_qwen3multi_numitems.pt", "train_qwen3sessionmoe.pt", "train_qwen3sessionmulti.pt"]
+
+
+@pytest.mark.parametrize("name", TRAIN)
+def test_forward_logits_loss_vs_golden(name):
+    g = load_golden(name)
+    m = build_model(g).eval()
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    extra = {} if g["num_items_in_batch"] is None else {"num_items_in_batch": g["num_items_in_batch"]}
+    with torch.no_grad():
+        out = m(**batch, **extra)
+    ref = g["logits"].to(DEV)
+    err = rel_err(out.logits, ref)
+    mx = (out.logits.float() - ref).abs().max().item()
+    print(f"{name}: logits rel {err:.3e} max|diff| {mx:.3e} (max|logit| {ref.abs().max().item():.2f}) "
+          f"loss {out.loss.item():.5f} vs {g['loss'].item():.5f}")
+    assert err <= 2e-2, err
+    assert mx <= 2e-2 * ref.abs().max().item() + 2e-2, mx
+    assert abs(out.loss.item() - g["loss"].item()) <= 5e-3 * max(1.0, abs(g["loss"].item()))
+    # logits without labels are NOT temperature scaled (Q7)
+    with torch.no_grad():
+        out2 = m(**{k: v for k, v in batch.items() if k != "labels"})
+    assert rel_err(out2.logits, ref * g["temperature"]) <= 2e-2
+    assert out2.loss is None
+
+
+@pytest.mark.parametrize("name", TRAIN)
+def test_backward_grads_vs_golden(name):
+    g = load_golden(name)
+    m = build_model(g).train()
+    m.config.dropout_rate = 0.0
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    extra = {} if g["num_items_in_batch"] is None else {"num_items_in_batch": g["num_items_in_batch"]}
+    out = m(**batch, **extra)
+    assert abs(out.loss.item() - g["loss"].item()) <= 5e-3 * max(1.0, abs(g["loss"].item()))
+    out.loss.backward()
+    params = dict(m.named_parameters())
+    worst = (0.0, None)
+    for k, d in g["grads"].items():
+        gr = params[k].grad
+        assert gr is not None, k
+        ref_norm = d["norm"].item()
+        rn = abs(gr.float().norm().item() - ref_norm) / (ref_norm + 1e-12)
+        if ref_norm > 1e-6:
+            worst = max(worst, (rn, k))
+            assert rn <= 3e-2, (k, rn, ref_norm)
+        s_ref = d["samples"].to(DEV)
+        mine = gr.float().reshape(-1)[::d["stride"]][: s_ref.numel()]
+        if int((s_ref != 0).sum()) >= 32 and s_ref.norm() > 1e-7:
+            cos = torch.nn.functional.cosine_similarity(mine, s_ref, dim=0).item()
+            assert cos >= 0.999, (k, cos)
+    eg = params["model.embed_tokens.weight"].grad
+    e = rel_err(eg, g["embed_grad"].to(DEV))
+    print(f"{name}: worst grad-norm rel diff {worst[0]:.3e} ({worst[1]}); embed grad rel {e:.3e}")
+    assert e <= 3e-2, e
+    assert torch.equal(m.lm_head.weight.grad, eg) or m.lm_head.weight is m.model.embed_tokens.weight
+
+
+def test_model_vs_oracle_left_padded_prefill():
+    """Left-padded eval-shaped batch (fully-masked pad query rows, Q1) through forward() vs the oracle."""
+    from gamer_b200 import synthetic as syn
+    from oracle import oracle_model as om
+    g = load_golden("decode_qwen3multi_lvl2.pt")
+    m = build_model(g, temperature=1.0).eval()
+    spec = spec_from_golden(g)
+    W = weights_from_golden(g)
+    b = g["batch"]
+    with torch.no_grad():
+        ref = om.forward(spec, W, b["input_ids"], b["attention_mask"], session_ids=b["session_ids"],
+                         extended_session_ids=b["extended_session_ids"], actions=b["actions"])["logits"]
+        out = m(**{k: v.to(DEV) for k, v in b.items()}, logits_to_keep=1)
+    assert out.logits.shape[1] == 1
+    assert rel_err(out.logits[:, 0], ref[:, -1].to(DEV)) <= 2e-2
+
+
+def test_state_dict_roundtrip_and_errors(tmp_path):
+    g = load_golden("train_qwen3multi.pt")
+    m = build_model(g)
+    m.save_pretrained(tmp_path)
+    m2 = type(m).from_pretrained(tmp_path).to(DEV)
+    assert m2.lm_head.weight.data_ptr() == m2.model.embed_tokens.weight.data_ptr()
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    with pytest.raises(ValueError):
+        m(input_ids=None)
+    with pytest.raises(RuntimeError):
+        m(input_ids=g["batch"]["input_ids"])       # CPU tensors: no fallback
