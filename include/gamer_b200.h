@@ -115,6 +115,23 @@ int gamer_ce_fwd_bwd(const float* logits, long long ld_l, const long long* label
                      const float* inv_norm, float grad_scale, float* loss_row, void* dlogits, long long ld_d,
                      gamer_stream_t stream);
 
+/* ---- K9: constrained beam-search decode ------------------------------------------------------------------------
+ * replaces, per generated token, HF GenerationMixin._beam_search + PrefixConstrainedLogitsProcessor + the Python Trie
+ * walk (SeqRec/tasks/test_SMB_decoder.py:159-177, SeqRec/generation/trie.py:5-104) and the cached attention of
+ * Qwen3MultiAttention.forward with DynamicCache (Qwen3Multi/model.py:118-143, masks :605-617,:717-728).
+ * The flat trie is CSR: node n has children [child_start[n], child_start[n+1]) with ascending child_tok[]. */
+int gamer_attn_decode(const void* qcur, const void* pk, const void* pv, long long ld_p, const void* gen_k,
+                      const void* gen_v, long long gen_step_stride, long long ld_g, const int* anc, int B, int beams,
+                      int L0, int n_gen, int n_q, int n_kv, int head_dim, int S_max, const int* am, const int* act,
+                      const int* sess, int mask_kind, const float* vmean, float scale, void* o, long long ld_o,
+                      gamer_stream_t stream);
+int gamer_trie_init(const long long* ids, int B, int L, int vocab, const unsigned char* last_set, const int* child_start,
+                    const int* child_tok, const int* child_node, int* node_out, gamer_stream_t stream);
+int gamer_beam_step(const float* logits, long long ld, int vocab, int n_users, int beams, const float* run_score,
+                    const int* node, const int* child_start, const int* child_tok, const int* child_node,
+                    int max_children, float* new_score, int* new_parent, int* new_tok, int* new_node, int* err,
+                    gamer_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

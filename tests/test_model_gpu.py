@@ -27,6 +27,7 @@ def build_model(g, temperature=None):
     cfg = Qwen3MoeConfig(**{k: v for k, v in c.items() if k != "rope_theta"})
     cfg.rope_theta = c["rope_theta"]
     cfg.mlp_type = "Qwen3"
+    cfg.moe_intermediate_size = c["hidden_size"]      # config/s2s-models/*/config.json: moe_intermediate_size == hidden_size
     cfg.Moe_behavior_only = False
     cfg.tie_word_embeddings = True
     cfg.use_behavior_token = True
@@ -37,7 +38,7 @@ def build_model(g, temperature=None):
     assert not unexpected and all(k == "lm_head.weight" for k in missing)
     m.tie_weights()
     m.set_hyper(temperature if temperature is not None else g.get("temperature", 1.0))
-    return m.to(DEV)
+    return m.to(DEV) if torch.cuda.is_available() else m
 
 
 def rel_err(a, b):
