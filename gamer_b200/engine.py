@@ -230,19 +230,21 @@ def _attention_fwd(arch, meta, x, norm_w, w_qkv, qn, kn, w_o, kind, tabs, act_id
     qe, ke, ve = embs if embs is not None else (None, None, None)
     rot = K.qk_norm_rope_fwd(raw, meta.L, arch.n_q, arch.n_kv, arch.head_dim, tabs[0], tabs[1], qn, kn, arch.eps,
                              pos_ids=meta.rope_pos, q_emb=qe, k_emb=ke, v_emb=ve, act_idx=act_idx)
-    o, lse = K.attn_fwd(rot, meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P, meta.am, meta.act,
-                        meta.sess, arch.head_dim ** -0.5)
+    o, lse, vmean = K.attn_fwd(rot, meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P, meta.am, meta.act,
+                               meta.sess, arch.head_dim ** -0.5)
     if gated:
         y = K.gemm_tn(o, w_o, arch.hidden)
         x_out = K.gate_residual_fwd(x, y, raw[:, arch.qkv_w:])
     else:
         y = None
         x_out = K.gemm_tn(o, w_o, arch.hidden, resid=x)
-    return x_out, dict(x=x, rstd=rstd, h=h, raw=raw, rot=rot, o=o, lse=lse, y=y)
+    return x_out, dict(x=x, rstd=rstd, h=h, raw=raw, rot=rot, o=o, lse=lse, y=y, vmean=vmean)
 
 
-def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save: bool):
-    """-> (final normed hidden [M,H] bf16, ctx).  ctx holds what the backward needs when save=True."""
+def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save: bool, kv_sink: list | None = None):
+    """-> (final normed hidden [M,H] bf16, ctx).  ctx holds what the backward needs when save=True.  `kv_sink` (decode
+    prefill) receives per layer {"self": (rot, vmean), "cross": (rot, vmean)} — the rotated q|k|v buffers double as the
+    prompt K/V cache."""
     B, L = meta.B, meta.L
     dev = input_ids.device
     x, pos_idx, beh_idx, act_idx = K.embed_route(input_ids, pack.emb, lut, arch.n_beh, arch.P, arch.pad, arch.eos)
@@ -288,6 +290,8 @@ def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save:
         x = x_out
         if save:
             ctx["layers"].append(saved)
+        if kv_sink is not None:
+            kv_sink.append({k: (saved[k]["rot"], saved[k]["vmean"]) for k in ("self", "cross") if k in saved})
     hidden, rstd = K.rmsnorm_fwd(x, pack.norm, arch.eps)
     if save:
         ctx["final"] = dict(x=x, rstd=rstd)

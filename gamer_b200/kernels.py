@@ -92,10 +92,11 @@ def rmsnorm_bwd(x, w, rstd, eps, dh, dw, row_map=None, dres=None, cat_idx=None, 
 
 
 def qk_norm_rope_fwd(raw, L, n_q, n_kv, hd, cos_tab, sin_tab, qn_w, kn_w, eps, pos_ids=None, pos0=0, q_emb=None,
-                     k_emb=None, v_emb=None, act_idx=None, width=None):
+                     k_emb=None, v_emb=None, act_idx=None, width=None, out=None):
     M = raw.shape[0]
     width = width if width is not None else (n_q + 2 * n_kv) * hd
-    out = torch.empty(M, width, dtype=BF16, device=raw.device)
+    if out is None:
+        out = torch.empty(M, width, dtype=BF16, device=raw.device)
     call("gamer_qk_norm_rope_fwd", ptr(raw), raw.stride(0), ptr(out), out.stride(0), M, L, n_q, n_kv, hd, ptr(pos_ids),
          pos0, ptr(cos_tab), ptr(sin_tab), ptr(qn_w), ptr(kn_w), ptr(q_emb), ptr(k_emb), ptr(v_emb), ptr(act_idx), eps,
          _stream())
@@ -145,7 +146,8 @@ def ref_gemm_tn(a, b, N, K):
 
 # ------------------------------------------------------------------------------------------------ K6
 def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
-    """qkv bf16 [B*L, ld]: q cols [0, n_q*hd), k next n_kv*hd, v next n_kv*hd.  -> (o [B*L, n_q*hd], lse [B,n_q,L])."""
+    """qkv bf16 [B*L, ld]: q cols [0, n_q*hd), k next n_kv*hd, v next n_kv*hd.
+    -> (o [B*L, n_q*hd], lse [B,n_q,L], vmean fp32 [B, n_kv, hd] = mean of all L value rows)."""
     dev = qkv.device
     ws = torch.empty(lib().gamer_attn_workspace_bytes(B, L, n_q, n_kv), dtype=torch.uint8, device=dev)
     o = torch.empty(B * L, n_q * hd, dtype=BF16, device=dev)
@@ -156,7 +158,7 @@ def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
     v = k + n_kv * hd * esz
     call("gamer_attn_fwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
          float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _stream())
-    return o, lse
+    return o, lse, ws.view(torch.float32).view(B, n_kv, hd)
 
 
 def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv):
@@ -217,3 +219,37 @@ def ce_fwd_bwd(logits, labels, V, inv_norm, grad_scale, dlogits=None, ignore_ind
     call("gamer_ce_fwd_bwd", ptr(logits), logits.stride(0), ptr(labels), R, V, ignore_index, ptr(inv_norm),
          float(grad_scale), ptr(loss_row), ptr(dlogits), 0 if dlogits is None else dlogits.stride(0), _stream())
     return loss_row
+
+
+# ------------------------------------------------------------------------------------------------ K9 decode
+def attn_decode(qcur, prompt_rot, gen, step_stride, anc, B, beams, L0, n_gen, n_q, n_kv, hd, S_max, am, act, sess, kind,
+                vmean, scale):
+    """qcur [R, ld_g] (this step's rotated q|k|v), prompt_rot [B*L0, ld_p], gen = base tensor of the per-step buffers."""
+    R = B * beams
+    o = torch.empty(R, n_q * hd, dtype=BF16, device=qcur.device)
+    esz = 2
+    koff, voff = n_q * hd * esz, (n_q + n_kv) * hd * esz
+    call("gamer_attn_decode", ptr(qcur), prompt_rot.data_ptr() + koff, prompt_rot.data_ptr() + voff, prompt_rot.stride(0),
+         gen.data_ptr() + koff, gen.data_ptr() + voff, step_stride, qcur.stride(0), ptr(anc), B, beams, L0, n_gen, n_q,
+         n_kv, hd, S_max, ptr(am), ptr(act), ptr(sess), kind, ptr(vmean), float(scale), ptr(o), o.stride(0), _stream())
+    return o
+
+
+def trie_init(ids, vocab, last_set, flat):
+    B, L = ids.shape
+    node = torch.empty(B, dtype=torch.int32, device=ids.device)
+    call("gamer_trie_init", ptr(ids), B, L, vocab, ptr(last_set), ptr(flat.child_start), ptr(flat.child_tok),
+         ptr(flat.child_node), ptr(node), _stream())
+    return node
+
+
+def beam_step(logits, vocab, n_users, beams, run_score, node, flat, err):
+    dev = logits.device
+    new_score = torch.empty(n_users, beams, dtype=torch.float32, device=dev)
+    new_parent = torch.empty(n_users, beams, dtype=torch.int32, device=dev)
+    new_tok = torch.empty_like(new_parent)
+    new_node = torch.empty_like(new_parent)
+    call("gamer_beam_step", ptr(logits), logits.stride(0), vocab, n_users, beams, ptr(run_score), ptr(node),
+         ptr(flat.child_start), ptr(flat.child_tok), ptr(flat.child_node), flat.max_children, ptr(new_score),
+         ptr(new_parent), ptr(new_tok), ptr(new_node), ptr(err), _stream())
+    return new_score, new_parent, new_tok, new_node

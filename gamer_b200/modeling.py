@@ -16,6 +16,11 @@ from transformers.models.qwen3_moe import Qwen3MoeConfig
 
 from . import engine as E
 
+try:  # transformers >= 5: flag-aware initialisers (skip parameters already loaded from a checkpoint)
+    from transformers import initialization as _init
+except ImportError:  # transformers 4.x (the reference's pin)
+    from torch.nn import init as _init
+
 
 class _Weight(nn.Module):
     """Parameter holder named like Qwen3RMSNorm (`.weight`, ones-initialised)."""
@@ -122,15 +127,18 @@ class _GamerCausalLM(PreTrainedModel):
 
     # ---- HF plumbing ---------------------------------------------------------------------------------------------
     def _init_weights(self, module):
+        # N(0, initializer_range) for Linear/Embedding, zeroed pad row, ones for the norms — as Qwen3PreTrainedModel
         std = self.config.initializer_range
         if isinstance(module, nn.Linear):
-            module.weight.data.normal_(mean=0.0, std=std)
+            _init.normal_(module.weight, mean=0.0, std=std)
         elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.padding_idx is not None:
-                module.weight.data[module.padding_idx].zero_()
+            loaded = getattr(module.weight, "_is_hf_initialized", False)
+            _init.normal_(module.weight, mean=0.0, std=std)
+            if module.padding_idx is not None and not loaded:
+                with torch.no_grad():
+                    module.weight[module.padding_idx].zero_()
         elif isinstance(module, _Weight):
-            module.weight.data.fill_(1.0)
+            _init.ones_(module.weight)
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
