@@ -92,7 +92,47 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def call(name: str, *args):
+# kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
+LAUNCHES = {"gamer_route_perm_build": 3, "gamer_embed_sort_build": 3, "gamer_attn_fwd": 2, "gamer_attn_bwd": 3}
+
+
+class Profile:
+    """Optional per-entry-point device timing (CUDA events on the launching stream) + algorithmic work counters."""
+
+    def __init__(self):
+        self.records = {}      # name -> list of (start_event, end_event, flops, bytes)
+        self.launches = 0
+
+    def summary(self):
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            out[name] = dict(calls=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs))
+        return out
+
+
+_PROFILE: Profile | None = None
+
+
+def set_profile(p: Profile | None):
+    global _PROFILE
+    _PROFILE = p
+
+
+def call(name: str, *args, work=(0, 0)):
     fn = getattr(lib(), name)
+    prof = _PROFILE
+    if prof is None:
+        check(fn(*args), name)
+        return
+    import torch
+    prof.launches += LAUNCHES.get(name, 1)
+    if prof.records is None:                      # count-only mode
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     rc = fn(*args)
+    e1.record()
     check(rc, name)
+    prof.records.setdefault(name, []).append((e0, e1, work[0], work[1]))

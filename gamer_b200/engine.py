@@ -171,6 +171,43 @@ class Pack:
             self.layers.append(d)
 
 
+class FlatPack(Pack):
+    """Pack built from the flat bf16 copy of the fused master buffer (written by the AdamW kernel): the forward
+    operands are plain views, only the transposed (dgrad) copies are materialised."""
+
+    def __init__(self, arch: Arch, flat_bf16: torch.Tensor, flat_f32: torch.Tensor):
+        a = arch
+        Wb = flat_views(a, flat_bf16)
+        Wf = flat_views(a, flat_f32)
+        self.emb = Wb["model.embed_tokens.weight"]
+        emb_t = torch.zeros(a.hidden, a.v_ld, dtype=BF16, device=self.emb.device)
+        emb_t[:, :a.vocab] = self.emb.t()
+        self.emb_t = emb_t
+        self.norm = Wf["model.norm.weight"]
+        self.layers = []
+        for l in range(a.n_layers):
+            p = f"L{l}."
+            d = {"in_norm": Wf[p + "in_norm"], "w_qkv": Wb[p + "w_qkv"], "w_o": Wb[p + "w_o"], "qn": Wf[p + "qn"],
+                 "kn": Wf[p + "kn"], "post_norm": Wf[p + "post_norm"]}
+            d["w_qkv_t"] = d["w_qkv"].t().contiguous()
+            d["w_o_t"] = d["w_o"].t().contiguous()
+            if l in a.cross:
+                d.update(ps_norm=Wf[p + "ps_norm"], c_w_qkvg=Wb[p + "c_w_qkvg"], c_w_o=Wb[p + "c_w_o"],
+                         c_qn=Wf[p + "c_qn"], c_kn=Wf[p + "c_kn"], c_qe=Wb[p + "c_qe"], c_ke=Wb[p + "c_ke"],
+                         c_ve=Wb[p + "c_ve"])
+                d["c_w_qkvg_t"] = d["c_w_qkvg"].t().contiguous()
+                d["c_w_o_t"] = d["c_w_o"].t().contiguous()
+            gu, dn = Wb[p + "w_gu"], Wb[p + "w_d"]                       # [E, 2I, Kf], [E, H, I]
+            E_, Kf = gu.shape[0], gu.shape[2]
+            d["w_gu"] = gu.view(E_ * 2 * a.inter, Kf)
+            d["w_gu_t"] = gu.transpose(1, 2).contiguous().view(E_ * Kf, 2 * a.inter)
+            d["w_d"] = dn.view(E_ * a.hidden, a.inter)
+            d["w_d_t"] = dn.transpose(1, 2).contiguous().view(E_ * a.inter, a.hidden)
+            if l in a.inject:
+                d["beh_emb"] = Wb[p + "beh_emb"]
+            self.layers.append(d)
+
+
 def rope_tables(arch: Arch, n_pos: int, device):
     """cos/sin [n_pos, head_dim/2] fp32, computed as Qwen3RotaryEmbedding does (fp32 outer product, then cos/sin)."""
     d = arch.head_dim
@@ -210,10 +247,11 @@ def make_meta(arch: Arch, input_ids, attention_mask, actions, session_ids, exten
         raise ValueError("`actions` is required by this backbone's behaviour-level attention mask")
     if need_sess and session_ids is None:
         raise AssertionError("Session IDs must be provided to generate session-wise causal mask.")
-    rope_pos, n_pos = None, L
+    # RoPE table rows: token positions 0..L-1 plus the few positions a decode call appends; extended session ids are
+    # < P * n_sessions <= L + P, so the same bound covers the session variants
+    rope_pos, n_pos = None, L + 2 * arch.P + 8
     if arch.session_rope() and extended_session_ids is not None:
         rope_pos = i32(extended_session_ids).view(-1)
-        n_pos = max(L, 5 * (L // arch.P + 2)) + 8     # ext ids are < P * n_sessions <= L; decode adds a few
     return BatchMeta(B, L, i32(attention_mask), i32(actions) if need_act else None,
                      i32(session_ids) if need_sess else None, rope_pos, n_pos)
 
@@ -402,34 +440,75 @@ def backward_stack(arch: Arch, pack: Pack, meta: BatchMeta, ctx, d_hidden, G: di
     return dx
 
 
-def grad_buffers(arch: Arch, device):
-    """Zeroed fp32 gradient buffers in the fused layouts the wgrad kernels write."""
-    z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=device)
-    G = {"model.embed_tokens.weight": z(arch.vocab, arch.hidden), "model.norm.weight": z(arch.hidden)}
+def fused_blocks(arch: Arch):
+    """Ordered (key, shape) list of the fused parameter blocks: the layout of the flat fp32 master-weight, gradient and
+    optimizer-state buffers.  Forward order, so one layer is one contiguous range (= one all-reduce bucket)."""
+    blocks = [("model.embed_tokens.weight", (arch.vocab, arch.hidden))]
     for l in range(arch.n_layers):
         p = f"L{l}."
         inject = l in arch.inject
         Kf = arch.hidden + (arch.beh_dim if inject else 0)
-        E = arch.n_exp if l in arch.sparse else 1
-        G[p + "in_norm"] = z(arch.hidden)
-        G[p + "w_qkv"] = z(arch.qkv_w, arch.hidden)
-        G[p + "w_o"] = z(arch.hidden, arch.q_w)
-        G[p + "qn"] = z(arch.head_dim)
-        G[p + "kn"] = z(arch.head_dim)
+        E_ = arch.n_exp if l in arch.sparse else 1
+        blocks += [(p + "in_norm", (arch.hidden,)), (p + "w_qkv", (arch.qkv_w, arch.hidden)),
+                   (p + "w_o", (arch.hidden, arch.q_w)), (p + "qn", (arch.head_dim,)), (p + "kn", (arch.head_dim,))]
         if l in arch.cross:
-            G[p + "ps_norm"] = z(arch.hidden)
-            G[p + "c_w_qkvg"] = z(arch.qkv_w + arch.hidden, arch.hidden)
-            G[p + "c_w_o"] = z(arch.hidden, arch.q_w)
-            G[p + "c_qn"] = z(arch.head_dim)
-            G[p + "c_kn"] = z(arch.head_dim)
-            G[p + "c_qe"] = z(arch.n_beh + 1, arch.q_w)
-            G[p + "c_ke"] = z(arch.n_beh + 1, arch.kv_w)
-            G[p + "c_ve"] = z(arch.n_beh + 1, arch.kv_w)
-        G[p + "post_norm"] = z(arch.hidden)
-        G[p + "w_gu"] = z(E, 2 * arch.inter, Kf)
-        G[p + "w_d"] = z(E, arch.hidden, arch.inter)
+            blocks += [(p + "ps_norm", (arch.hidden,)), (p + "c_w_qkvg", (arch.qkv_w + arch.hidden, arch.hidden)),
+                       (p + "c_w_o", (arch.hidden, arch.q_w)), (p + "c_qn", (arch.head_dim,)),
+                       (p + "c_kn", (arch.head_dim,)), (p + "c_qe", (arch.n_beh + 1, arch.q_w)),
+                       (p + "c_ke", (arch.n_beh + 1, arch.kv_w)), (p + "c_ve", (arch.n_beh + 1, arch.kv_w))]
+        blocks += [(p + "post_norm", (arch.hidden,)), (p + "w_gu", (E_, 2 * arch.inter, Kf)),
+                   (p + "w_d", (E_, arch.hidden, arch.inter))]
         if inject:
-            G[p + "beh_emb"] = z(arch.n_beh + 1, arch.beh_dim)
+            blocks += [(p + "beh_emb", (arch.n_beh + 1, arch.beh_dim))]
+    blocks += [("model.norm.weight", (arch.hidden,))]
+    return blocks
+
+
+def flat_views(arch: Arch, flat: torch.Tensor) -> dict:
+    """{fused key: view} over a flat buffer laid out by `fused_blocks` (every block start is 16-byte aligned)."""
+    out, off = {}, 0
+    for key, shape in fused_blocks(arch):
+        n = 1
+        for s in shape:
+            n *= s
+        out[key] = flat[off:off + n].view(*shape)
+        off += (n + 3) // 4 * 4
+    return out
+
+
+def flat_size(arch: Arch) -> int:
+    off = 0
+    for _, shape in fused_blocks(arch):
+        n = 1
+        for s in shape:
+            n *= s
+        off += (n + 3) // 4 * 4
+    return off
+
+
+def layer_ranges(arch: Arch):
+    """[(name, start, end)] element ranges of the flat layout: embedding, each layer, final norm — the gradient buckets."""
+    ranges, off, cur, cur_start = [], 0, None, 0
+    for key, shape in fused_blocks(arch):
+        n = 1
+        for s in shape:
+            n *= s
+        grp = key.split(".")[0] if key.startswith("L") else key
+        if grp != cur:
+            if cur is not None:
+                ranges.append((cur, cur_start, off))
+            cur, cur_start = grp, off
+        off += (n + 3) // 4 * 4
+    ranges.append((cur, cur_start, off))
+    return ranges
+
+
+def grad_buffers(arch: Arch, device, flat: torch.Tensor | None = None):
+    """Fused fp32 gradient buffers (views of one flat allocation) in the layouts the wgrad kernels write."""
+    if flat is None:
+        flat = torch.zeros(flat_size(arch), dtype=torch.float32, device=device)
+    G = flat_views(arch, flat)
+    G["_flat"] = flat
     return G
 
 
@@ -498,35 +577,44 @@ def lm_head_backward(arch: Arch, pack: Pack, hidden, shifted, scale_dev, tempera
     return d_hidden
 
 
+def loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature):
+    """Forward of the training step.  Returns (loss, state for `loss_backward`)."""
+    hidden, saved = forward_stack(arch, pack, input_ids, meta, lut, save=True)
+    loss = lm_head_loss(arch, pack, hidden, shifted, inv_norm, temperature)
+    sort_buf = K.embed_sort(input_ids.view(-1), arch.vocab, arch.pad)
+    return loss, dict(saved=saved, hidden=hidden, shifted=shifted, inv_norm=inv_norm, temperature=temperature,
+                      sort_buf=sort_buf, meta=meta)
+
+
+def loss_backward(arch, pack, st, grad_out, G, on_layer_done=None):
+    """Backward of the training step into the fused gradient buffers G (accumulating).  grad_out: device scalar."""
+    scale = (grad_out.float().reshape(()) * st["inv_norm"].view(())).reshape(1).contiguous()
+    d_hidden = lm_head_backward(arch, pack, st["hidden"], st["shifted"], scale, st["temperature"],
+                                G["model.embed_tokens.weight"])
+    dx0 = backward_stack(arch, pack, st["meta"], st["saved"], d_hidden, G, on_layer_done=on_layer_done)
+    K.embed_bwd(dx0, arch.vocab, st["sort_buf"], G["model.embed_tokens.weight"])
+    if on_layer_done is not None:
+        on_layer_done(-1)
+    st["saved"] = None
+
+
 class DecoderLossFunction(torch.autograd.Function):
     """loss = CE(lm_head(decoder(input_ids)) / T).  Inputs after the fixed arguments are the fp32 master parameters in
-    `param_names(arch)` order; backward returns their gradients."""
+    `param_names(arch)` order; backward returns their gradients (views of one flat fused buffer)."""
 
     @staticmethod
     def forward(ctx, arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, hooks, *params):
-        hidden, saved = forward_stack(arch, pack, input_ids, meta, lut, save=True)
-        loss = lm_head_loss(arch, pack, hidden, shifted, inv_norm, temperature)
-        sort_buf = K.embed_sort(input_ids.view(-1), arch.vocab, arch.pad)
-        ctx.arch, ctx.pack, ctx.meta, ctx.saved, ctx.hooks = arch, pack, meta, saved, hooks
-        ctx.hidden, ctx.shifted, ctx.inv_norm, ctx.temperature, ctx.sort_buf = hidden, shifted, inv_norm, temperature, sort_buf
-        ctx.n_params = len(params)
+        loss, st = loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature)
+        ctx.arch, ctx.pack, ctx.st, ctx.hooks = arch, pack, st, hooks
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        arch, pack, meta = ctx.arch, ctx.pack, ctx.meta
-        dev = ctx.hidden.device
-        G = grad_buffers(arch, dev)
-        scale = (grad_out.float() * ctx.inv_norm.view(())).reshape(1).contiguous()
-        d_hidden = lm_head_backward(arch, pack, ctx.hidden, ctx.shifted, scale, ctx.temperature,
-                                    G["model.embed_tokens.weight"])
+        arch = ctx.arch
+        G = grad_buffers(arch, ctx.st["hidden"].device)
         on_done = ctx.hooks.get("on_layer_done") if ctx.hooks else None
-        dx0 = backward_stack(arch, pack, meta, ctx.saved, d_hidden, G,
-                             on_layer_done=(lambda l: on_done(l, G)) if on_done else None)
-        K.embed_bwd(dx0, arch.vocab, ctx.sort_buf, G["model.embed_tokens.weight"])
-        if on_done:
-            on_done(-1, G)
+        loss_backward(arch, ctx.pack, ctx.st, grad_out, G, on_layer_done=(lambda l: on_done(l, G)) if on_done else None)
         named = unfuse_grads(arch, G)
         grads = tuple(named[n] for n in param_names(arch))
-        ctx.saved = None
+        ctx.st = None
         return (None,) * 9 + grads

@@ -38,7 +38,8 @@ def embed_route(ids, table_bf16, beh_lut, n_beh, tokens_per_item, pad, eos, ctx=
     if ctx is not None:
         ctx = ctx.contiguous()
     call("gamer_embed_route_fwd", ptr(ids), ptr(ctx), 0 if ctx is None else ctx.shape[1], B, S, pos0, tokens_per_item,
-         pad, eos, V, ptr(beh_lut), n_beh, ptr(table_bf16), H, ptr(x), ptr(pos), ptr(beh), ptr(act), _stream())
+         pad, eos, V, ptr(beh_lut), n_beh, ptr(table_bf16), H, ptr(x), ptr(pos), ptr(beh), ptr(act), _stream(),
+         work=(0, B * S * (8 + 2 * H + 12)))        # id + bf16 row + 3 int32 indices per token (§8d)
     return x, pos, beh, act
 
 
@@ -67,7 +68,8 @@ def embed_bwd(dx, vocab, sort_buf, dtable=None):
     M, H = dx.shape
     if dtable is None:
         dtable = torch.zeros(vocab, H, dtype=torch.float32, device=dx.device)
-    call("gamer_embed_bwd", ptr(dx), M, H, vocab, ptr(sort_buf), ptr(dtable), _stream())
+    call("gamer_embed_bwd", ptr(dx), M, H, vocab, ptr(sort_buf), ptr(dtable), _stream(),
+         work=(0, M * (4 + 2 * H) + vocab * H * 4))
     return dtable
 
 
@@ -125,7 +127,8 @@ def gemm_tn(a, b, N, K=None, rows=None, n_groups=1, seg_off=None, out=None, out_
                           device=a.device)
     call("gamer_gemm_bf16_tn", ptr(a), a.stride(0), rows, ptr(b), b.stride(0), n_groups, N, K, ptr(seg_off), ptr(out),
          out.stride(0), 1 if out.dtype == torch.float32 else 0, ptr(resid), 0 if resid is None else resid.stride(0),
-         ptr(row_map), float(alpha), _stream())
+         ptr(row_map), float(alpha), _stream(),
+         work=(2 * rows * N * K, rows * K * 2 + n_groups * N * K * 2 + rows * N * out.element_size()))
     return out
 
 
@@ -134,7 +137,7 @@ def gemm_wgrad(dy, x, N_out, K_in, dw, rows=None, n_groups=1, seg_off=None):
     rows = dy.shape[0] if rows is None else rows
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     call("gamer_gemm_bf16_wgrad", ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, N_out, K_in, n_groups, ptr(seg_off),
-         ptr(dw), _stream())
+         ptr(dw), _stream(), work=(2 * rows * N_out * K_in, rows * (N_out + K_in) * 2 + n_groups * N_out * K_in * 4))
     return dw
 
 
@@ -157,7 +160,8 @@ def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
     k = q + n_q * hd * esz
     v = k + n_kv * hd * esz
     call("gamer_attn_fwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
-         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _stream())
+         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _stream(),
+         work=(4 * hd * n_q * B * L * (L + 1) // 2, B * L * (2 * n_q + 2 * n_kv) * hd * 2))   # causal pair count (§8d)
     return o, lse, ws.view(torch.float32).view(B, n_kv, hd)
 
 
@@ -172,7 +176,8 @@ def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scal
     dk = dq + n_q * hd * esz
     dv = dk + n_kv * hd * esz
     call("gamer_attn_bwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
-         float(scale), ptr(o), ptr(d_o), o.stride(0), ptr(lse), ptr(ws), dq, dk, dv, dqkv.stride(0), _stream())
+         float(scale), ptr(o), ptr(d_o), o.stride(0), ptr(lse), ptr(ws), dq, dk, dv, dqkv.stride(0), _stream(),
+         work=(10 * hd * n_q * B * L * (L + 1) // 2, B * L * (4 * n_q + 4 * n_kv) * hd * 2))
     return dqkv
 
 

@@ -1,0 +1,141 @@
+"""Native training step for the drop-in models: forward + backward + gradient all-reduce + AdamW on flat buffers.
+
+The reference trains through HF `Trainer` (SeqRec/tasks/train_SMB_decoder.py:396-447): torch DDP bucketed all-reduce,
+`clip_grad_norm_(1.0)`, `adamw_torch`, cosine schedule with warm-up, gradient accumulation with the loss normalised by
+`num_items_in_batch`.  `accelerate` is not installed here, so HF Trainer cannot run; this module is the
+loop underneath it, restated B200-first:
+
+  * all master weights live in ONE flat fp32 buffer laid out by `engine.fused_blocks` (q|k|v and gate|up stacked the way
+    the GEMMs read them); every HF parameter is a view of it, so state dicts / checkpoints are unchanged;
+  * gradients are accumulated by the wgrad kernels straight into a flat fp32 buffer of the same layout; one layer = one
+    contiguous range = one NCCL all-reduce bucket, launched (async, NCCL's stream) as soon as that layer's backward
+    kernels are enqueued, so the reduction of layer l overlaps the backward of layers l-1..0;
+  * one fused AdamW kernel updates p/m/v and emits the bf16 operand copy for the next step's GEMMs.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+from ._cabi import call, ptr
+from .distributed import BucketReducer
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NativeTrainer:
+    def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
+                 warmup_steps=0, total_steps=None, process_group=None, min_lr_ratio=0.0):
+        self.model = model
+        self.arch = model.arch
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("NativeTrainer needs the model on a CUDA device (no CPU path)")
+        self.dev = dev
+        a = self.arch
+        n = E.flat_size(a)
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        # re-point every parameter at its slice of the flat buffer (checkpoint keys and shapes unchanged)
+        views = E.unfuse_grads(a, E.flat_views(a, self.flat_p))
+        params = dict(model.named_parameters())
+        with torch.no_grad():
+            for k, p in params.items():
+                views[k].copy_(p.data)
+                p.data = views[k]
+        # HF Trainer: no weight decay on norm weights (get_decay_parameter_names); embeddings and linears decay
+        mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+        mviews = E.unfuse_grads(a, E.flat_views(a, mask))
+        for k in params:
+            leaf = k.split(".")[-2]
+            if not ("norm" in leaf or "layernorm" in leaf):
+                mviews[k].fill_(1)
+        self.decay_mask = mask
+        self.G = E.grad_buffers(a, dev, self.flat_g)
+        self.ranges = E.layer_ranges(a)
+        self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.warmup_steps, self.total_steps, self.min_lr_ratio = warmup_steps, total_steps, min_lr_ratio
+        self.step_idx = 0
+        self.pg = process_group
+        self.reducer = BucketReducer(self.flat_g, self.ranges, process_group)
+        self.world = self.reducer.world
+        self.hp_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.hp = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lut = E.behaviour_lut(a, dev)
+        call("gamer_cast_f32_bf16", ptr(self.flat_p), ptr(self.flat_bf16), n, _stream())
+        self.pack = E.FlatPack(a, self.flat_bf16, self.flat_p)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def current_lr(self):
+        """HF `cosine` schedule with linear warm-up (get_cosine_schedule_with_warmup)."""
+        s = self.step_idx
+        if self.warmup_steps and s < self.warmup_steps:
+            return self.lr * s / max(1, self.warmup_steps)
+        if not self.total_steps:
+            return self.lr
+        prog = (s - self.warmup_steps) / max(1, self.total_steps - self.warmup_steps)
+        return self.lr * max(self.min_lr_ratio, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+
+    def _bucket_hook(self, layer_idx):
+        """Called right after layer `layer_idx`'s backward kernels were enqueued (n_layers = final norm, -1 = embedding):
+        start that bucket's all-reduce; NCCL's stream waits on everything enqueued so far and runs beside the rest of
+        the backward."""
+        a = self.arch
+        self.reducer.launch("model.norm.weight" if layer_idx == a.n_layers else
+                            ("model.embed_tokens.weight" if layer_idx < 0 else f"L{layer_idx}"))
+
+    def forward_backward(self, batch, inv_norm, last_micro=True):
+        a = self.arch
+        ids = batch["input_ids"].contiguous()
+        meta = E.make_meta(a, ids, batch.get("attention_mask"), batch.get("actions"), batch.get("session_ids"),
+                           batch.get("extended_session_ids"))
+        shifted = E.shift_labels(batch["labels"])
+        loss, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature))
+        one = torch.ones((), dtype=torch.float32, device=self.dev)
+        E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=self._bucket_hook if last_micro else None)
+        return loss
+
+    def step(self, batch, micro_batch=None):
+        """One optimizer step over `batch` (device tensors, [B, L]); `micro_batch` splits it for gradient accumulation
+        with the HF `num_items_in_batch` normalisation (sum of CE over the window / number of label tokens)."""
+        B = batch["input_ids"].shape[0]
+        mb = B if not micro_batch else min(micro_batch, B)
+        shifted_all = E.shift_labels(batch["labels"])
+        inv_norm = (1.0 / (shifted_all != -100).sum().clamp(min=1).float()).reshape(1)
+        self.flat_g.zero_()
+        total = torch.zeros((), dtype=torch.float32, device=self.dev)
+        starts = list(range(0, B, mb))
+        for i, b0 in enumerate(starts):
+            sub = {k: v[b0:b0 + mb] for k, v in batch.items() if torch.is_tensor(v)}
+            total = total + self.forward_backward(sub, inv_norm, last_micro=(i == len(starts) - 1))
+        self.reducer.wait_all()
+        self.optimizer_step()
+        return total
+
+    def optimizer_step(self):
+        n = self.flat_p.numel()
+        self.step_idx += 1
+        t = self.step_idx
+        self.hp_host[0] = self.current_lr()
+        self.hp_host[1] = 1.0 - self.betas[0] ** t
+        self.hp_host[2] = 1.0 - self.betas[1] ** t
+        self.hp.copy_(self.hp_host, non_blocking=True)
+        gn = None
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            self.gnorm_sq.zero_()
+            call("gamer_sumsq_accumulate", ptr(self.flat_g), n, ptr(self.gnorm_sq), _stream())
+            gn = self.gnorm_sq
+        call("gamer_adamw_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v),
+             ptr(self.decay_mask), ptr(self.flat_bf16), n, ptr(self.hp), self.betas[0], self.betas[1], self.eps,
+             self.wd, ptr(gn), float(self.max_grad_norm or 0.0), 1.0 / self.world, _stream())
+        self.pack = E.FlatPack(self.arch, self.flat_bf16, self.flat_p)
+        self.model._pack = None                    # the kernel wrote the weights behind autograd's back

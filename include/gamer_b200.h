@@ -132,6 +132,15 @@ int gamer_beam_step(const float* logits, long long ld, int vocab, int n_users, i
                     int max_children, float* new_score, int* new_parent, int* new_tok, int* new_node, int* err,
                     gamer_stream_t stream);
 
+/* ---- optimizer over the flat fused parameter buffer ------------------------------------
+ * AdamW as HF Trainer configures it (SeqRec/tasks/train_SMB_decoder.py:396-428: adamw_torch, weight decay on non-norm
+ * weights, clip_grad_norm_(max_grad_norm)).  hp (device floats): lr, 1-beta1^t, 1-beta2^t. */
+int gamer_sumsq_accumulate(const float* g, long long n, float* out, gamer_stream_t stream);
+int gamer_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* decay_mask, void* p_bf16,
+                     long long n, const float* hp, float beta1, float beta2, float eps, float weight_decay,
+                     const float* gnorm_sq, float max_grad_norm, float grad_scale, gamer_stream_t stream);
+int gamer_cast_f32_bf16(const float* src, void* dst, long long n, gamer_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
