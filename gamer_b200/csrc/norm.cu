@@ -61,11 +61,12 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    float wv[8], dwacc[8];
+    float wv[8], dwacc[8], catacc[4][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         wv[i] = w[lane * 8 + i];
         dwacc[i] = 0.f;
+        catacc[0][i] = catacc[1][i] = catacc[2][i] = catacc[3][i] = 0.f;
     }
     for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
         float xf[8], df[8];
@@ -104,9 +105,26 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
             float cf[8];
             bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + H256 + lane * 8), cf);
             const int r = cat_idx[m];
+            if (r < 4) {                       // register partials for the (<= 4) behaviour rows, flushed once below
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&scat[r * cat_dim + lane * 8 + i], cf[i]);
+                for (int q = 0; q < 4; ++q)
+                    if (q == r) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) catacc[q][i] += cf[i];
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(&scat[r * cat_dim + lane * 8 + i], cf[i]);
+            }
         }
+    }
+    if (dcat != nullptr && lane < cat_dim / 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < cat_rows) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(&scat[q * cat_dim + lane * 8 + i], catacc[q][i]);
+            }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) atomicAdd(&sdw[lane * 8 + i], dwacc[i]);
@@ -197,11 +215,16 @@ __global__ void qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw
 }
 
 // backward: d_out (grad wrt rotated q,k and v) -> d_raw; accumulates d qn_w / d kn_w and the behaviour-embedding grads.
-__global__ void qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw,
-                                        const bf16* __restrict__ dout, long long ld_dout, bf16* __restrict__ draw,
-                                        long long ld_draw, float* __restrict__ d_qn_w, float* __restrict__ d_kn_w,
-                                        float* __restrict__ d_q_emb, float* __restrict__ d_k_emb,
-                                        float* __restrict__ d_v_emb, int emb_rows) {
+// Every 8-lane group keeps ONE head for the whole kernel (group g -> head g % n_heads, tokens strided), so the
+// norm-weight and behaviour-embedding partial sums live in registers ([emb_rows <= 4][8 columns] per lane) and are
+// flushed once per thread: no per-token atomics.
+constexpr int MAX_EMB_ROWS = 4;
+
+__global__ void __launch_bounds__(256)
+qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw, const bf16* __restrict__ dout,
+                        long long ld_dout, bf16* __restrict__ draw, long long ld_draw, float* __restrict__ d_qn_w,
+                        float* __restrict__ d_kn_w, float* __restrict__ d_q_emb, float* __restrict__ d_k_emb,
+                        float* __restrict__ d_v_emb, int emb_rows) {
     extern __shared__ float sh[];  // [2*64] norm-weight grads | [emb_rows * (n_q + 2 n_kv) * 64] embedding grads
     const int n_heads = a.n_q + 2 * a.n_kv;
     const int emb_w = n_heads * HD;
@@ -211,84 +234,99 @@ __global__ void qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw
     for (int i = threadIdx.x; i < 2 * HD + (has_emb ? emb_rows * emb_w : 0); i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
     const int sub = threadIdx.x & 7;
-    const long long groups = a.M * n_heads;
-    const long long gid0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long gstride = ((long long)gridDim.x * blockDim.x) >> 3;
-    // trip count padded so that all 8 lanes of a group (and all groups of a warp) stay convergent for the shuffles
-    const long long iters = (groups + gstride - 1) / gstride;
-    float dwq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // this lane's 8 norm-weight columns
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;      // launch guarantees n_groups % n_heads == 0
+    const int h = (int)(group % n_heads);
+    const long long m0 = group / n_heads, m_stride = n_groups / n_heads;
+    const long long iters = (a.M + m_stride - 1) / m_stride;
+    const int col = h * HD + sub * 8;
+    const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
+    const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
+    const int width = is_q ? a.n_q * HD : a.n_kv * HD;
+    const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
+    const float* wn = is_q ? a.qn_w : a.kn_w;
+    float wv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = wn[sub * 8 + i];
+    float dwn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float demb[MAX_EMB_ROWS][8];
+#pragma unroll
+    for (int r = 0; r < MAX_EMB_ROWS; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) demb[r][i] = 0.f;
+
     for (long long it = 0; it < iters; ++it) {
-        const long long gidx = gid0 + it * gstride;
-        const bool live = gidx < groups;
-        const long long m = live ? gidx / n_heads : 0;
-        const int h = live ? (int)(gidx % n_heads) : 0;
-        const int col = h * HD + sub * 8;
-        const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
+        const long long mm = m0 + it * m_stride;
+        const bool live = mm < a.M;
+        const long long m = live ? mm : 0;
         float u[8], d[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(raw + m * ld_raw + col), u);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + m * ld_dout + col), d);
         const int act = (has_emb && live) ? a.act_idx[m] : 0;
         if (has_emb) {
-            const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
-            const int width = is_q ? a.n_q * HD : a.n_kv * HD;
-            const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
             float e[8];
             bf16x8_to_float(*reinterpret_cast<const bf16x8*>(emb + (long long)act * width + hc), e);
 #pragma unroll
             for (int i = 0; i < 8; ++i) u[i] += e[i];
         }
         float du[8];
-        {
-            const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
-            const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
-            const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
-            const float* wn = is_q ? a.qn_w : a.kn_w;
-            float ss = 0.f;
+        const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
+        const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
+        const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
+        float ss = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ss += u[i] * u[i];
-            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-            const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
-            float dn[8], dot = 0.f;
+        for (int i = 0; i < 8; ++i) ss += u[i] * u[i];
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
+        float dn[8], dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float partner = __shfl_xor_sync(0xffffffffu, d[i], 4);
+            // transpose of the rotation: first half gets +sin * d[second], second half gets -sin * d[first]
+            dn[i] = d[i] * ct[i] + ((sub < 4) ? partner : -partner) * st[i];
+            const float g = wv[i] * dn[i];
+            dot += g * u[i];
+            du[i] = g;
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        dot *= (1.0f / HD) * rstd * rstd * rstd;
+        if (is_q || is_k) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float partner = __shfl_xor_sync(0xffffffffu, d[i], 4);
-                // transpose of the rotation: first half gets +sin * d[second], second half gets -sin * d[first]
-                dn[i] = d[i] * ct[i] + ((sub < 4) ? partner : -partner) * st[i];
-                const float g = wn[sub * 8 + i] * dn[i];
-                dot += g * u[i];
-                du[i] = g;
+                dwn[i] += live ? dn[i] * u[i] * rstd : 0.f;
+                du[i] = rstd * du[i] - u[i] * dot;
             }
-            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-            dot *= (1.0f / HD) * rstd * rstd * rstd;
-            if (is_q || is_k) {
+        } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float gw = live ? dn[i] * u[i] * rstd : 0.f;
-                    dwq[i] += is_q ? gw : 0.f;
-                    dwk[i] += is_q ? 0.f : gw;
-                    du[i] = rstd * du[i] - u[i] * dot;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) du[i] = d[i];
-            }
+            for (int i = 0; i < 8; ++i) du[i] = d[i];
         }
         if (live) {
             *reinterpret_cast<bf16x8*>(draw + m * ld_draw + col) = float_to_bf16x8(du);
             if (has_emb) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(&semb[act * emb_w + col + i], du[i]);
+                for (int r = 0; r < MAX_EMB_ROWS; ++r)
+                    if (r == act) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) demb[r][i] += du[i];
+                    }
             }
         }
     }
+    if (is_q || is_k) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sdw[sub * 8 + i], dwq[i]);
-        atomicAdd(&sdw[HD + sub * 8 + i], dwk[i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(&sdw[(is_q ? 0 : HD) + sub * 8 + i], dwn[i]);
+    }
+    if (has_emb) {
+#pragma unroll
+        for (int r = 0; r < MAX_EMB_ROWS; ++r)
+            if (r < emb_rows) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(&semb[r * emb_w + col + i], demb[r][i]);
+            }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < HD; i += blockDim.x) {
@@ -386,9 +424,13 @@ extern "C" int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const v
     GAMER_REQUIRE(!has_emb || (d_q_emb && d_k_emb && d_v_emb), "behaviour-embedding grads missing");
     const size_t smem = (2 * HD + (has_emb ? emb_rows * (n_q + 2 * n_kv) * HD : 0)) * sizeof(float);
     GAMER_REQUIRE(smem <= 48 * 1024, "too many behaviour rows for the shared-memory accumulator");
-    const long long groups = M * (n_q + 2 * n_kv);
-    const long long blocks = (groups * 8 + 255) / 256;
-    const int grid = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
+    GAMER_REQUIRE(!has_emb || emb_rows <= MAX_EMB_ROWS, "at most %d behaviour-embedding rows (num_behavior + 1)", MAX_EMB_ROWS);
+    // 32 groups per block; the number of groups must be a multiple of n_heads so each group keeps one head
+    const int n_heads = n_q + 2 * n_kv;
+    int grid = 148 * 4;
+    const long long want = (M * n_heads + 31) / 32;
+    if (want < grid) grid = (int)want;
+    grid = (grid + n_heads - 1) / n_heads * n_heads;      // 32 * grid divisible by n_heads when grid is
     qk_norm_rope_bwd_kernel<<<grid, 256, smem, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
                                                          reinterpret_cast<const bf16*>(dout), ld_dout,
                                                          reinterpret_cast<bf16*>(draw), ld_draw, d_qn_w, d_kn_w,

@@ -113,6 +113,46 @@ def decode_step(arch, pack, lut, meta, state, tokens, s):
     return E.lm_head_logits(arch, pack, hidden)
 
 
+def beam_search_core(B, beams, S, vocab, flat, node0, logits0, advance, device):
+    """The beam bookkeeping, independent of where the logits come from.
+
+    node0 [B] int32: trie node of every user's prompt suffix; logits0 [B*beams, >=vocab] fp32: next-token logits of the
+    (identical) beams of each user; advance(s, parent_rows [R] int64, tokens [R] int64) -> logits [R, >=vocab] for the
+    rows obtained by appending `tokens` to the hypotheses `parent_rows`.
+    Returns (generated tokens [B, beams, S] int64, summed log-probabilities [B, beams] fp32), best-first per user.
+    """
+    R = B * beams
+    node = node0.repeat_interleave(beams).contiguous()
+    run = torch.zeros(B, beams, dtype=torch.float32, device=device)
+    run[:, 1:] = -1e9                                                        # HF: beam_scores[:, 1:] = -1e9
+    err = torch.zeros(1, dtype=torch.int32, device=device)
+    toks, parents = [], []
+    row_base = (torch.arange(B, device=device) * beams).view(B, 1)
+    logits = logits0
+    for s in range(S):
+        run, parent, tok, node = K.beam_step(logits, vocab, B, beams, run, node, flat, err)
+        toks.append(tok)
+        parents.append(parent)
+        if s + 1 == S:
+            break
+        prow = (parent.long() + row_base).view(-1)                           # parent row of every new beam row
+        logits = advance(s, prow, tok.view(-1).long())
+        node = node.view(-1).contiguous()
+    code = int(err.item())                                                   # single host sync of the whole decode
+    if code == 1:
+        raise ValueError("`prefix_allowed_tokens_fn` returned an empty list for a beam: the prompt suffix is not a "
+                         "prefix of any candidate (cf. PrefixConstrainedLogitsProcessor)")
+    if code == 2:
+        raise RuntimeError("beam step candidate buffer overflow")
+    # backtrack the token choices through the parent pointers
+    gen = torch.empty(B, beams, S, dtype=torch.long, device=device)
+    idx = torch.arange(beams, device=device).view(1, beams).expand(B, beams)
+    for s in reversed(range(S)):
+        gen[:, :, s] = torch.gather(toks[s].long(), 1, idx)
+        idx = torch.gather(parents[s].long(), 1, idx)
+    return gen, run
+
+
 @torch.no_grad()
 def constrained_beam_search(model, input_ids, attention_mask, session_ids, extended_session_ids, actions,
                             max_new_tokens, prefix_allowed_tokens_fn, candidate_trie, num_beams, num_return_sequences,
@@ -137,8 +177,8 @@ def constrained_beam_search(model, input_ids, attention_mask, session_ids, exten
     sink = []
     hidden, ctx = E.forward_stack(arch, pack, input_ids, meta, lut, save=False, kv_sink=sink)
     last_hidden = hidden.view(B, L0, -1)[:, -1, :].contiguous()
-    logits = E.lm_head_logits(arch, pack, last_hidden)                       # [B, V] fp32
-    logits = logits.repeat_interleave(beams, dim=0).contiguous()             # beams of a user start identical
+    logits0 = E.lm_head_logits(arch, pack, last_hidden)                      # [B, V] fp32
+    logits0 = logits0.repeat_interleave(beams, dim=0).contiguous()           # beams of a user start identical
 
     state = dict(B=B, beams=beams, L0=L0, S_max=S, tabs=ctx["tabs"], prompt=sink,
                  ctx=input_ids.repeat_interleave(beams, dim=0).contiguous(),
@@ -151,41 +191,16 @@ def constrained_beam_search(model, input_ids, attention_mask, session_ids, exten
     if arch.session_rope() and extended_session_ids is not None:
         # Qwen3SessionMoe/model.py:688-701: the s-th new token is rotated at max(extended_session_ids) + 1 + s
         state["rope_next"] = (extended_session_ids.max(dim=-1)[0] + 1).repeat_interleave(beams)
+    own_rows = torch.arange(R, dtype=torch.int32, device=dev)
 
-    node = K.trie_init(input_ids, arch.vocab, last_bitmap, flat).repeat_interleave(beams).contiguous()
-    run = torch.zeros(B, beams, dtype=torch.float32, device=dev)
-    run[:, 1:] = -1e9
-    err = torch.zeros(1, dtype=torch.int32, device=dev)
-    toks, parents = [], []
-    row_base = (torch.arange(B, device=dev) * beams).view(B, 1)
-    for s in range(S):
-        run, parent, tok, node = K.beam_step(logits, arch.vocab, B, beams, run, node, flat, err)
-        toks.append(tok)
-        parents.append(parent)
-        if s + 1 == S:
-            break
-        prow = (parent.long() + row_base).view(-1)                           # parent row of every new beam row
+    def advance(s, prow, tokens):
         anc = state["anc"].index_select(0, prow)
-        anc[:, s] = torch.arange(R, dtype=torch.int32, device=dev)           # this step's K/V is stored at its own slot
+        anc[:, s] = own_rows                                                 # this step's K/V is stored at its own slot
         state["anc"] = anc.contiguous()
-        if state["rope_next"] is not None:
-            pass                                                             # per-user value: identical for all beams
-        logits = decode_step(arch, pack, lut, meta, state, tok.view(-1).long(), s)
-        node = node.view(-1).contiguous()
+        return decode_step(arch, pack, lut, meta, state, tokens, s)
 
-    code = int(err.item())                                                   # single host sync of the whole decode
-    if code == 1:
-        raise ValueError("`prefix_allowed_tokens_fn` returned an empty list for a beam: the prompt suffix is not a "
-                         "prefix of any candidate (cf. PrefixConstrainedLogitsProcessor)")
-    if code == 2:
-        raise RuntimeError("beam step candidate buffer overflow")
-
-    # ---- backtrack the token choices through the parent pointers --------------------------------------------------
-    gen = torch.empty(B, beams, S, dtype=torch.long, device=dev)
-    idx = torch.arange(beams, device=dev).view(1, beams).expand(B, beams)
-    for s in reversed(range(S)):
-        gen[:, :, s] = torch.gather(toks[s].long(), 1, idx)
-        idx = torch.gather(parents[s].long(), 1, idx)
+    node0 = K.trie_init(input_ids, arch.vocab, last_bitmap, flat)
+    gen, run = beam_search_core(B, beams, S, arch.vocab, flat, node0, logits0, advance, dev)
     seqs = torch.cat([input_ids.view(B, 1, L0).expand(B, beams, L0), gen], dim=2)
     scores = run / float(S)                                                  # length_penalty = 1: sum / generated length
     nret = num_return_sequences

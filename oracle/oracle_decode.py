@@ -91,6 +91,21 @@ def constrained_beam_search(spec: om.Spec, W: dict, tree: PrefixTree, last_token
     return seqs.reshape(B * K, -1), scores.reshape(-1)
 
 
+def teacher_forced_scores(spec: om.Spec, W: dict, input_ids, attention_mask, gen_tokens, session_ids=None,
+                          extended_session_ids=None, actions=None):
+    """Score given continuations with the cached path: mean full-vocabulary log-probability of `gen_tokens` [R, S]
+    appended to `input_ids` [R, L] (= what beam search reports for a hypothesis that survives)."""
+    logits, st = om.prefill(spec, W, input_ids, attention_mask, session_ids, extended_session_ids, actions)
+    R, S = gen_tokens.shape
+    total = torch.zeros(R)
+    for s in range(S):
+        logp = torch.log_softmax(logits.float(), dim=-1)
+        total = total + logp.gather(1, gen_tokens[:, s:s + 1]).squeeze(1)
+        if s + 1 < S:
+            logits = om.decode_step(spec, W, st, gen_tokens[:, s])
+    return total / float(S)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # evaluation/ranking.py restated on id tuples (the reference compares decoded strings; ids are a bijection)
 # ------------------------------------------------------------------------------------------------------------

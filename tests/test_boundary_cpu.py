@@ -52,3 +52,29 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_seqrec_facade_paths_in_subprocess():
+    """The reference's import paths resolve to the drop-in classes (own process: `SeqRec` must not be the reference's)."""
+    code = (
+        "from SeqRec.models.generative.Qwen3Multi import Qwen3MultiWithTemperature as A\n"
+        "from SeqRec.models.generative.Qwen3SessionMoe import Qwen3SessionMoeWithTemperature as B\n"
+        "from SeqRec.models.generative.Qwen3SessionMulti import Qwen3SessionMultiWithTemperature as C\n"
+        "from SeqRec.generation.trie import Trie, prefix_allowed_tokens_fn_by_last_token\n"
+        "from SeqRec.evaluation.ranking import get_topk_results, get_metrics_results\n"
+        "import gamer_b200.modeling as m\n"
+        "assert A is m.Qwen3MultiWithTemperature and B is m.Qwen3SessionMoeWithTemperature\n"
+        "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_ranking_matches_reference_golden():
+    from gamer_b200 import ranking
+    g = load_golden("decode_qwen3multi_lvl2.pt")
+    K = g["num_beams"]
+    hits = ranking.get_topk_results(g["rank_pred"], g["sequences_scores"], g["rank_targets"], K)
+    assert hits == g["rank_hits"]
+    met = ranking.get_metrics_results(hits, g["rank_names"], g["rank_targets"])
+    for k, v in g["rank_metrics"].items():
+        assert abs(met[k] - v) < 1e-12, k

@@ -16,42 +16,85 @@ SCORE_TOL = 3e-2      # |mean log-prob| differences (bf16 vs fp32), scores are ~
 TIE_GAP = 8e-2
 
 
-def _check_against(ref_seqs, ref_scores, seqs, scores, B, K, L0, flat_items):
-    ref_seqs, seqs = ref_seqs.view(B, K, -1), seqs.cpu().view(B, K, -1)
-    ref_scores, scores = ref_scores.view(B, K), scores.cpu().view(B, K)
-    n_same_rank, n_total = 0, 0
+def _check_generate(spec, W, batch, items, K, out, ref_seqs=None, ref_scores=None):
+    """(1) every decoded tuple is a catalogue item, rows are best-first and distinct, the prompt is returned untouched;
+    (2) each returned hypothesis re-scored by the oracle's cached teacher-forced path agrees within SCORE_TOL — this
+        covers the numerics of prefill + every decode step without depending on which near-tied prefixes survived;
+    (3) against a reference beam (golden or oracle): the best hypothesis matches when its margin exceeds TIE_GAP, and the
+        two beams overlap (pruning of near-tied prefixes under bf16 noise may swap the tail)."""
+    B, L0 = batch["input_ids"].shape
+    seqs, scores = out.sequences.cpu().view(B, K, -1), out.sequences_scores.cpu().view(B, K)
+    flat_items = set(tuple(r[1:]) for r in items.tolist())
+    rep = lambda t: None if t is None else t.repeat_interleave(K, dim=0)
     for b in range(B):
-        assert torch.equal(seqs[b, :, :L0], ref_seqs[b, :, :L0])                       # prompt returned untouched
-        mine = {tuple(seqs[b, k, L0:].tolist()): scores[b, k].item() for k in range(K)}
-        ref = [(tuple(ref_seqs[b, k, L0:].tolist()), ref_scores[b, k].item()) for k in range(K)]
-        assert all(t in flat_items for t in mine), "decoded tuple outside the candidate set"
-        assert len(mine) == K
-        assert all(scores[b, k] >= scores[b, k + 1] for k in range(K - 1))             # best-first
-        # every hypothesis the reference ranks clearly inside the beam must be found, with a close score
-        worst_kept = ref[-1][1]
-        for k, (t, sc) in enumerate(ref):
-            if sc - worst_kept > TIE_GAP or t in mine:
-                assert t in mine, (b, k, t, sc)
-                assert abs(mine[t] - sc) <= SCORE_TOL, (b, k, mine[t], sc)
-            prev_gap = ref[k - 1][1] - sc if k > 0 else 1e9
-            next_gap = sc - ref[k + 1][1] if k + 1 < K else 1e9
-            if min(prev_gap, next_gap) > TIE_GAP:
-                n_total += 1
-                n_same_rank += int(tuple(seqs[b, k, L0:].tolist()) == t)
-    assert n_same_rank == n_total, (n_same_rank, n_total)
-    return n_total
+        assert torch.equal(seqs[b, :, :L0], batch["input_ids"][b].expand(K, L0))
+        tuples = [tuple(seqs[b, k, L0:].tolist()) for k in range(K)]
+        assert all(t in flat_items for t in tuples) and len(set(tuples)) == K
+        assert all(scores[b, k] >= scores[b, k + 1] for k in range(K - 1))
+    with torch.no_grad():
+        rescored = od.teacher_forced_scores(spec, W, rep(batch["input_ids"]), rep(batch["attention_mask"]),
+                                            seqs.reshape(B * K, -1)[:, L0:], rep(batch["session_ids"]),
+                                            rep(batch["extended_session_ids"]), rep(batch["actions"])).view(B, K)
+    worst = (rescored - scores).abs().max().item()
+    assert worst <= SCORE_TOL, worst
+    overlap = 0
+    if ref_seqs is not None:
+        ref_seqs, ref_scores = ref_seqs.view(B, K, -1), ref_scores.view(B, K)
+        for b in range(B):
+            mine = set(tuple(seqs[b, k, L0:].tolist()) for k in range(K))
+            ref = [tuple(ref_seqs[b, k, L0:].tolist()) for k in range(K)]
+            overlap += len(mine & set(ref))
+            if ref_scores[b, 0] - ref_scores[b, 1] > TIE_GAP:
+                assert tuple(seqs[b, 0, L0:].tolist()) == ref[0], (b, ref[0])
+        assert overlap >= 0.6 * B * K, overlap / (B * K)
+    return worst, overlap / (B * K) if ref_seqs is not None else None
+
+
+def _trie_fn(items, pad):
+    from gamer_b200.trie import Trie, prefix_allowed_tokens_fn_by_last_token
+    last = set(int(t) for t in items[:, -1]) | {pad}
+    return prefix_allowed_tokens_fn_by_last_token(Trie(items.tolist()), last), last
+
+
+@pytest.mark.parametrize("name", ["decode_qwen3multi_lvl2.pt", "decode_qwen3multi_lvl1.pt"])
+def test_beam_driver_bit_exact_on_fp32_logits(name):
+    """The GPU beam machinery (flat trie walk, fused log-softmax + mask + top-K, parent backtracking) fed with the
+    oracle's fp32 logits must reproduce the reference's HF generate output BIT-EXACTLY (tuples) and its scores to 1e-5."""
+    from gamer_b200 import kernels as k
+    from gamer_b200.generation import _resolve_constraint, beam_search_core
+    from oracle import oracle_model as om
+    g = load_golden(name)
+    spec, W = spec_from_golden(g), weights_from_golden(g)
+    cat = syn.make_catalogue(g["catalogue_size"], g["catalogue_seed"])
+    items = cat.item_sequences(g["target_behavior"])
+    fn, _ = _trie_fn(items, spec.pad)
+    b, K = g["batch"], g["num_beams"]
+    B, L0 = b["input_ids"].shape
+    flat, bitmap = _resolve_constraint(fn, None, spec.vocab_size, spec.pad, torch.device(DEV))
+    rep = lambda t: t.repeat_interleave(K, dim=0)
+    with torch.no_grad():
+        logits0, st = om.prefill(spec, W, rep(b["input_ids"]), rep(b["attention_mask"]), rep(b["session_ids"]),
+                                 rep(b["extended_session_ids"]), rep(b["actions"]))
+
+    def advance(s, prow, tokens):
+        with torch.no_grad():
+            st.reorder(prow.cpu())
+            return om.decode_step(spec, W, st, tokens.cpu()).to(DEV).contiguous()
+
+    node0 = k.trie_init(b["input_ids"].to(DEV), spec.vocab_size, bitmap, flat)
+    gen, run = beam_search_core(B, K, 4, spec.vocab_size, flat, node0, logits0.to(DEV).contiguous(), advance, torch.device(DEV))
+    assert torch.equal(gen.cpu().view(B * K, 4), g["sequences"][:, L0:])
+    assert torch.allclose((run / 4).cpu().view(-1), g["sequences_scores"], atol=1e-5, rtol=0)
 
 
 @pytest.mark.parametrize("name", ["decode_qwen3multi_lvl2.pt", "decode_qwen3multi_lvl1.pt"])
 def test_generate_vs_reference_golden(name):
-    from gamer_b200.trie import Trie, prefix_allowed_tokens_fn_by_last_token
     g = load_golden(name)
     m = build_model(g, temperature=1.0).eval()
+    spec, W = spec_from_golden(g), weights_from_golden(g)
     cat = syn.make_catalogue(g["catalogue_size"], g["catalogue_seed"])
     items = cat.item_sequences(g["target_behavior"])
-    trie = Trie(items.tolist())
-    last = set(int(t) for t in items[:, -1]) | {m.config.pad_token_id}
-    fn = prefix_allowed_tokens_fn_by_last_token(trie, last)
+    fn, _ = _trie_fn(items, spec.pad)
     b = {k: v.to(DEV) for k, v in g["batch"].items()}
     K = g["num_beams"]
     out = m.generate(input_ids=b["input_ids"], attention_mask=b["attention_mask"], session_ids=b["session_ids"],
@@ -60,10 +103,8 @@ def test_generate_vs_reference_golden(name):
                      return_dict_in_generate=True, early_stopping=True)
     B, L0 = b["input_ids"].shape
     assert out.sequences.shape == (B * K, L0 + 4) and out.sequences.dtype == torch.int64
-    flat_items = set(tuple(r[1:]) for r in items.tolist())
-    n = _check_against(g["sequences"], g["sequences_scores"], out.sequences, out.sequences_scores, B, K, L0, flat_items)
-    print(f"{name}: {n} rank-checked hypotheses; max |score diff| "
-          f"{(out.sequences_scores.cpu() - g['sequences_scores']).abs().max().item():.3e}")
+    worst, overlap = _check_generate(spec, W, g["batch"], items, K, out, g["sequences"], g["sequences_scores"])
+    print(f"{name}: worst |score - oracle rescoring| {worst:.3e}; beam overlap with the reference {overlap:.2f}")
 
 
 @pytest.mark.parametrize("variant_golden,target", [("train_qwen3sessionmoe.pt", 2), ("train_qwen3sessionmulti.pt", 0),
@@ -71,26 +112,22 @@ def test_generate_vs_reference_golden(name):
 def test_generate_vs_oracle(variant_golden, target):
     """Session variants (the reference's own generate() does not run for Qwen3SessionMoe under the installed
     transformers) and the lowest-level target (fully masked cross rows, Q1/Q3) against the oracle."""
-    from gamer_b200.trie import Trie, prefix_allowed_tokens_fn_by_last_token
     g = load_golden(variant_golden)
     m = build_model(g, temperature=1.0).eval()
-    spec = spec_from_golden(g)
-    W = weights_from_golden(g)
+    spec, W = spec_from_golden(g), weights_from_golden(g)
     cat = syn.make_catalogue(3000, 1)
     batch, _ = syn.make_eval_batch(cat, 5, max_his_len=14, target_behavior=target, seed=21, median_len=7)
     items = cat.item_sequences(target)
-    last = set(int(t) for t in items[:, -1]) | {spec.pad}
+    fn, last = _trie_fn(items, spec.pad)
     K = 10
     with torch.no_grad():
         ref_seqs, ref_scores = od.constrained_beam_search(
             spec, W, od.PrefixTree(items.tolist()), last, batch["input_ids"], batch["attention_mask"],
             batch["session_ids"], batch["extended_session_ids"], batch["actions"], num_beams=K)
-    fn = prefix_allowed_tokens_fn_by_last_token(Trie(items.tolist()), last)
     b = {k: v.to(DEV) for k, v in batch.items()}
     out = m.generate(**b, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
-    B, L0 = batch["input_ids"].shape
-    flat_items = set(tuple(r[1:]) for r in items.tolist())
-    _check_against(ref_seqs, ref_scores, out.sequences, out.sequences_scores, B, K, L0, flat_items)
+    worst, overlap = _check_generate(spec, W, batch, items, K, out, ref_seqs, ref_scores)
+    print(f"{variant_golden} target {target}: worst |score - oracle rescoring| {worst:.3e}; overlap {overlap:.2f}")
 
 
 def test_beam_step_kernel_vs_torch():
