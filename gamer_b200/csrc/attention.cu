@@ -12,6 +12,9 @@
 // backward (the analytic gradient of that uniform softmax, = the reference's eager-attention gradient).
 //
 // Math runs on mma.sync.m16n8k16 bf16 tiles with fp32 accumulation and an online softmax in the exp2 domain.
+#include <stdlib.h>
+
+#include "attention_tc.cuh"
 #include "common.cuh"
 
 namespace {
@@ -643,11 +646,22 @@ int check_common(int n_q, int n_kv, int head_dim, int kind, const int* act, cons
     return 0;
 }
 
+// tcgen05 path (attention_tc.cu) unless the shape is outside its specialisation or GAMER_ATTN_LEGACY=1 (A/B testing)
+bool use_tc(int L, int n_q, int n_kv, int head_dim) {
+    static int legacy = -1;
+    if (legacy < 0) {
+        const char* e = getenv("GAMER_ATTN_LEGACY");
+        legacy = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return legacy == 0 && attn_tc_supported(L, n_q, n_kv, head_dim);
+}
+long long vmean_bytes(int B, int n_kv) { return ((long long)B * n_kv * D * sizeof(float) + 255) / 256 * 256; }
+
 }  // namespace
 
 extern "C" long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv) {
-    // vmean [B, n_kv, 64] fp32
-    return (long long)B * n_kv * D * sizeof(float);
+    // vmean [B, n_kv, 64] fp32 first (callers read it back), then the tensor-core path's key codes
+    return vmean_bytes(B, n_kv) + attn_tc_fwd_ws_bytes(B, L);
 }
 
 extern "C" int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
@@ -664,6 +678,9 @@ extern "C" int gamer_attn_fwd(const void* q, const void* k, const void* v, long 
     a.o = reinterpret_cast<bf16*>(o); a.ld_o = ld_o; a.lse = lse;
     v_colmean_kernel<<<B * n_kv, 256, 0, stream>>>(a.v, ld, L, n_kv, reinterpret_cast<float*>(workspace));
     GAMER_LAUNCH_CHECK();
+    if (use_tc(L, n_q, n_kv, head_dim))
+        return attn_tc_fwd(q, k, v, ld, B, L, n_q, n_kv, mask_kind, tokens_per_item, am, act, sess, scale, a.vmean,
+                           reinterpret_cast<uint8_t*>(workspace) + vmean_bytes(B, n_kv), o, ld_o, lse, stream);
     dim3 grid((L + BQ - 1) / BQ, n_q, B);
     static bool cfg = false;
     if (!cfg) {
@@ -683,7 +700,9 @@ extern "C" int gamer_attn_fwd(const void* q, const void* k, const void* v, long 
 
 extern "C" long long gamer_attn_bwd_workspace_bytes(int B, int L, int n_q) {
     const int q_tiles = (L + BQ - 1) / BQ;
-    return (long long)B * n_q * L * sizeof(float) + (long long)B * q_tiles * sizeof(int);
+    const long long legacy = (long long)B * n_q * L * sizeof(float) + (long long)B * q_tiles * sizeof(int);
+    const long long tc = attn_tc_bwd_ws_bytes(B, L, n_q);
+    return legacy > tc ? legacy : tc;
 }
 
 extern "C" int gamer_attn_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
@@ -693,6 +712,9 @@ extern "C" int gamer_attn_bwd(const void* q, const void* k, const void* v, long 
                               cudaStream_t stream) {
     if (int e = check_common(n_q, n_kv, head_dim, mask_kind, act, sess)) return e;
     if (B == 0 || L == 0) return 0;
+    if (use_tc(L, n_q, n_kv, head_dim))
+        return attn_tc_bwd(q, k, v, ld, B, L, n_q, n_kv, mask_kind, tokens_per_item, am, act, sess, scale, o, d_o, ld_o, lse,
+                           workspace, dq, dk, dv, ld_d, stream);
     const int q_tiles = (L + BQ - 1) / BQ;
     float* dsum = reinterpret_cast<float*>(workspace);
     int* uni = reinterpret_cast<int*>(dsum + (long long)B * n_q * L);

@@ -1,0 +1,1069 @@
+// K6 on the 5th-gen tensor cores: session / behaviour-masked attention, forward and fused backward, GQA 2:1, head_dim 64.
+//
+// Every matrix product (QK^T, PV, dO V^T, P^T dO, dS^T Q, dS K) is a tcgen05.mma over 128x128 (or 128x64) tiles with
+// TMA-staged SWIZZLE_128B operands and TMEM accumulators; the softmax / mask / dS arithmetic runs in dedicated warps that
+// read the score tiles from TMEM (one query row per thread) and hand P / dS back through shared memory.
+//
+//   forward  : CTA = (sequence, kv head, 128-query tile).  The two query heads of the GQA group ping-pong: while the
+//              softmax warpgroup of head A works on tile t, the tensor core computes S_B(t) / O_B += P_B V, so the MUFU and
+//              the tensor pipe overlap.  Online softmax with a lazy rescale (the running max is only raised — and O only
+//              rescaled, on a cold path — when it would grow by more than 2^64; P stays representable in bf16).
+//   backward : CTA = (sequence, kv head, 128-key tile); loops over (head of the group, query tile).  dK and dV accumulate
+//              in TMEM over the whole loop; dQ tiles leave through a TMA fp32 reduce-add into a tile-major accumulator.
+//
+// Mask predicate (reference: SeqRec/models/generative/Qwen3Multi/model.py:573-741, Qwen3SessionMoe/model.py:416-468) is
+// evaluated per (query, key) from per-key codes that fold the key padding mask in (attn_meta_kernel).  Rows with no
+// allowed key are "uniform rows" (quirk Q1): forward output = column mean of V over all L keys, lse = +inf; backward uses
+// P = 1/L over all keys (the analytic gradient of that uniform softmax).
+#include "attention_tc.cuh"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int D = 64;
+constexpr int BT = 128;               // tile edge: queries and keys
+constexpr int TILE_BYTES = BT * D * 2;  // 16 KB: one [128 x 64] bf16 SWIZZLE_128B tile
+constexpr int KC_MAX = 0x7fffffff;
+
+template <int KIND>
+__host__ __device__ constexpr bool kind_causal() { return KIND == MASK_CAUSAL || KIND == MASK_MULTI_CROSS; }
+template <int KIND>
+__host__ __device__ constexpr bool kind_uses_act() { return KIND == MASK_MULTI_CROSS || KIND == MASK_SESSION_CROSS; }
+template <int KIND>
+__host__ __device__ constexpr bool kind_uses_sess() { return KIND == MASK_SESSION || KIND == MASK_SESSION_CROSS; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-key codes: ka = valid ? act : MAX, ks = valid ? sess : MAX (valid = j < L and attention_mask[j]); tile flag = all
+// 128 keys of the tile valid.  One block per (sequence, key tile).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void attn_meta_kernel(const int* __restrict__ am, const int* __restrict__ act, const int* __restrict__ sess,
+                                 int L, int Lp, int k_tiles, int* __restrict__ ka, int* __restrict__ ks,
+                                 int* __restrict__ tflag) {
+    const int b = blockIdx.x / k_tiles, t = blockIdx.x % k_tiles;
+    const int j = t * BT + threadIdx.x;
+    bool valid = false;
+    int a = KC_MAX, s = KC_MAX;
+    if (j < L) {
+        const long long idx = (long long)b * L + j;
+        valid = am[idx] != 0;
+        if (valid) {
+            a = act ? act[idx] : 0;
+            s = sess ? sess[idx] : 0;
+        }
+    }
+    ka[(long long)b * Lp + j] = a;
+    ks[(long long)b * Lp + j] = s;
+    const int all = __syncthreads_and(valid ? 1 : 0);
+    if (threadIdx.x == 0) tflag[blockIdx.x] = all;
+}
+
+template <int KIND, bool DIAG>
+__device__ __forceinline__ bool allow_tc(int ka, int ks, int act_i, int sess_i, int c, int row, int j, int i, int istart) {
+    if constexpr (KIND == MASK_CAUSAL) {
+        bool ok = (ka == 0);
+        if (DIAG) ok = ok && (c <= row);
+        return ok;
+    } else if constexpr (KIND == MASK_MULTI_CROSS) {
+        bool ok = (ka < act_i);
+        if (DIAG) ok = ok && (c <= row);
+        return ok;
+    } else if constexpr (KIND == MASK_SESSION) {
+        return (ks < sess_i) || (j >= istart && j <= i && ks != KC_MAX);
+    } else {
+        return (ks < sess_i) && (ka < act_i);
+    }
+}
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return umma_desc_sw128(saddr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) { return umma_desc_sw128(saddr, lbo, 1024); }
+
+// D[128 x 128] = A[128 x 64] B[128 x 64]^T, both K-major tiles (k = head dim)
+__device__ __forceinline__ void issue_nt_128x128x64(uint32_t d_tmem, uint32_t sa, uint32_t sb) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, desc_k(sa + k * 32), desc_k(sb + k * 32), idesc, k != 0);
+}
+// D[128 x 64] (+)= A[128 x 128] B[128 x 64]: A K-major in two 64-wide halves (16 KB apart), B MN-major [128 k-rows x 64]
+__device__ __forceinline__ void issue_nn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        umma_bf16(d_tmem, desc_k(sa + (k >> 2) * TILE_BYTES + (k & 3) * 32), desc_mn(sb + k * 2048, TILE_BYTES), idesc,
+                  (acc || k != 0) ? 1u : 0u);
+}
+// D[128 x 64] (+)= A^T B with A stored [128 k-rows x 128 m] (two 64-wide halves, MN-major) and B [128 k-rows x 64] MN-major
+__device__ __forceinline__ void issue_tn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        umma_bf16(d_tmem, desc_mn(sa + k * 2048, TILE_BYTES), desc_mn(sb + k * 2048, TILE_BYTES), idesc,
+                  (acc || k != 0) ? 1u : 0u);
+}
+
+// cold path of the online softmax: multiply this thread's O row (64 fp32 TMEM columns) by alpha
+__device__ __noinline__ void rescale_o_row(uint32_t t_o, float alpha) {
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + hh * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+        tmem_st_32x32(t_o + hh * 32, o);
+    }
+    tmem_st_wait();
+}
+
+// =================================================================================================================
+// forward
+// =================================================================================================================
+constexpr int F_STAGES = 3;
+constexpr int F_META_BYTES = 1024;                             // ka[128] | ks[128]
+constexpr int F_STAGE_BYTES = 2 * TILE_BYTES + F_META_BYTES;   // K | V | codes
+constexpr int F_OFF_Q = 0;                                     // 2 heads
+constexpr int F_OFF_KV = 2 * TILE_BYTES;
+constexpr int F_OFF_P = F_OFF_KV + F_STAGES * F_STAGE_BYTES;   // 2 heads x 2 halves
+constexpr int F_OFF_BAR = F_OFF_P + 4 * TILE_BYTES;
+constexpr int F_SMEM = F_OFF_BAR + 256 + 1024;
+constexpr int F_THREADS = 384;
+
+struct FwdParams {
+    int B, L, Lp, n_q, n_kv, P, q_tiles, k_tiles, total;
+    const int* ka;
+    const int* ks;
+    const int* tflag;
+    const int* act;
+    const int* sess;
+    float scale_log2;
+    const float* vmean;
+    float* lse;
+};
+
+template <int KIND>
+__device__ __forceinline__ void fwd_decode(int w, const FwdParams& p, int& b, int& g, int& qt, int& T) {
+    const int per = p.B * p.n_kv;
+    qt = p.q_tiles - 1 - w / per;  // heaviest (most key tiles) first
+    const int rem = w % per;
+    b = rem / p.n_kv;
+    g = rem % p.n_kv;
+    T = kind_causal<KIND>() ? min(qt + 1, p.k_tiles) : p.k_tiles;
+}
+
+// mask + row max over the 128 scores of one tile held in registers
+template <int KIND, bool DIAG>
+__device__ __forceinline__ float mask_max(uint32_t (&s)[128], const int4* mk4, int act_i, int sess_i, int row, int j0, int i,
+                                          int istart) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c4 = 0; c4 < 32; ++c4) {
+        int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
+        if (KIND != MASK_SESSION) a4 = mk4[c4];
+        if (kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
+        const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            const bool ok = allow_tc<KIND, DIAG>(av[e], sv[e], act_i, sess_i, c, row, j0 + c, i, istart);
+            const float v = ok ? __uint_as_float(s[c]) : -INFINITY;
+            s[c] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+        }
+    }
+    return mx;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(F_THREADS, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;                 // [F_STAGES]
+    uint64_t* kv_empty = kv_full + F_STAGES;      // [F_STAGES]
+    uint64_t* s_full = kv_empty + F_STAGES;       // [2]
+    uint64_t* p_full = s_full + 2;                // [2]
+    uint64_t* o_full = p_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmQ);
+        prefetch_tmap(&tmK);
+        prefetch_tmap(&tmV);
+        prefetch_tmap(&tmO);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < F_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(&s_full[h], 1);
+            mbar_init(&p_full[h], 128);
+            mbar_init(&o_full[h], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0, item_par = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+                int b, g, qt, T;
+                fwd_decode<KIND>(w, p, b, g, qt, T);
+                mbar_wait(q_empty, item_par ^ 1);
+                mbar_expect_tx(q_full, 2 * TILE_BYTES);
+                tma_load_3d(smem + F_OFF_Q, &tmQ, q_full, (2 * g) * D, qt * BT, b);
+                tma_load_3d(smem + F_OFF_Q + TILE_BYTES, &tmQ, q_full, (2 * g + 1) * D, qt * BT, b);
+                for (int t = 0; t < T; ++t) {
+                    mbar_wait(&kv_empty[st], ph ^ 1);
+                    uint8_t* sk = smem + F_OFF_KV + st * F_STAGE_BYTES;
+                    mbar_expect_tx(&kv_full[st], F_STAGE_BYTES);
+                    tma_load_3d(sk, &tmK, &kv_full[st], g * D, t * BT, b);
+                    tma_load_3d(sk + TILE_BYTES, &tmV, &kv_full[st], g * D, t * BT, b);
+                    bulk_load_1d(sk + 2 * TILE_BYTES, p.ka + (long long)b * p.Lp + t * BT, 512, &kv_full[st]);
+                    bulk_load_1d(sk + 2 * TILE_BYTES + 512, p.ks + (long long)b * p.Lp + t * BT, 512, &kv_full[st]);
+                    if (++st == F_STAGES) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+                item_par ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0, item_par = 0, tile_n = 0;
+            const uint32_t sq = smem_u32(smem + F_OFF_Q);
+            const uint32_t sp = smem_u32(smem + F_OFF_P);
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+                int b, g, qt, T;
+                fwd_decode<KIND>(w, p, b, g, qt, T);
+                mbar_wait(q_full, item_par);
+                mbar_wait(&kv_full[st], ph);
+                tc_fence_after();
+                {
+                    const uint32_t sk = smem_u32(smem + F_OFF_KV + st * F_STAGE_BYTES);
+                    issue_nt_128x128x64(tmem_base + 0, sq, sk);
+                    umma_commit(&s_full[0]);
+                    issue_nt_128x128x64(tmem_base + 128, sq + TILE_BYTES, sk);
+                    umma_commit(&s_full[1]);
+                    if (T == 1) umma_commit(q_empty);  // Q is dead once the item's last S tiles are done
+                }
+                for (int t = 0; t < T; ++t) {
+                    int nst = st + 1;
+                    uint32_t nph = ph;
+                    if (nst == F_STAGES) {
+                        nst = 0;
+                        nph ^= 1;
+                    }
+                    const uint32_t sv = smem_u32(smem + F_OFF_KV + st * F_STAGE_BYTES + TILE_BYTES);
+                    const uint32_t skn = smem_u32(smem + F_OFF_KV + nst * F_STAGE_BYTES);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&p_full[h], tile_n & 1);
+                        tc_fence_after();
+                        if (t + 1 < T) {
+                            if (h == 0) {
+                                mbar_wait(&kv_full[nst], nph);
+                                tc_fence_after();
+                            }
+                            issue_nt_128x128x64(tmem_base + h * 128, sq + h * TILE_BYTES, skn);
+                            umma_commit(&s_full[h]);
+                            if (h == 1 && t + 2 == T) umma_commit(q_empty);
+                        }
+                        issue_nn_128x64x128(tmem_base + 256 + h * 64, sp + h * 2 * TILE_BYTES, sv, t > 0);
+                        umma_commit(&o_full[h]);
+                    }
+                    umma_commit(&kv_empty[st]);
+                    st = nst;
+                    ph = nph;
+                    ++tile_n;
+                }
+                item_par ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== softmax warpgroups: warps 4-7 = head A, 8-11 = head B =====================
+        const int wg = (warp - 4) >> 2;
+        const int wq = warp & 3;  // TMEM lane quarter of this warp
+        const int row = wq * 32 + lane;
+        const uint32_t t_s = tmem_base + ((uint32_t)(wq * 32) << 16) + wg * 128;
+        const uint32_t t_o = tmem_base + ((uint32_t)(wq * 32) << 16) + 256 + wg * 64;
+        uint8_t* sP = smem + F_OFF_P + wg * 2 * TILE_BYTES;
+        int st = 0;
+        uint32_t ph = 0, tile_n = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+            int b, g, qt, T;
+            fwd_decode<KIND>(w, p, b, g, qt, T);
+            const int h = 2 * g + wg;
+            const int i = qt * BT + row;
+            int act_i = 0, sess_i = 0;
+            if (i < p.L) {
+                if (kind_uses_act<KIND>()) act_i = p.act[(long long)b * p.L + i];
+                if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
+            }
+            const int istart = (i / p.P) * p.P;
+            float m = -INFINITY, l = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const int* meta = reinterpret_cast<const int*>(smem + F_OFF_KV + st * F_STAGE_BYTES + 2 * TILE_BYTES);
+                bool need_mask = true;
+                const bool diag = kind_causal<KIND>() && (t == qt);
+                if (KIND == MASK_CAUSAL) need_mask = diag || (p.tflag[b * p.k_tiles + t] == 0);
+                mbar_wait(&kv_full[st], ph);  // key codes of this stage (already complete: the S MMA waited on it)
+                mbar_wait(&s_full[wg], tile_n & 1);
+                tc_fence_after();
+                uint32_t s[128];
+                tmem_ld_32x32(t_s, s);
+                tmem_ld_32x32(t_s + 32, s + 32);
+                tmem_ld_32x32(t_s + 64, s + 64);
+                tmem_ld_32x32(t_s + 96, s + 96);
+                tmem_ld_wait();
+                float mx = -INFINITY;
+                if (need_mask) {
+                    const int4* mk4 = reinterpret_cast<const int4*>(meta);
+                    if (diag) mx = mask_max<KIND, true>(s, mk4, act_i, sess_i, row, t * BT, i, istart);
+                    else mx = mask_max<KIND, false>(s, mk4, act_i, sess_i, row, t * BT, i, istart);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+                }
+                // lazy running max (log2 domain): raise it only from -inf or by more than 2^64
+                const float m_tile = mx * p.scale_log2;
+                float m_new = m;
+                if (m == -INFINITY) m_new = m_tile;
+                else if (m_tile > m + 64.f) m_new = m_tile;
+                const bool rescale = (m != -INFINITY) && (m_new != m);
+                if (t > 0) {
+                    mbar_wait(&o_full[wg], (tile_n - 1) & 1);  // PV(t-1) done: O stable, P buffer free
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, rescale)) rescale_o_row(t_o, rescale ? ex2_approx(m - m_new) : 1.f);
+                }
+                if (rescale) l *= ex2_approx(m - m_new);
+                m = m_new;
+                const float neg_m = (m == -INFINITY) ? 0.f : -m;
+                float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 128; c += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
+                    sum0 += p0;
+                    sum1 += p1;
+                    s[c >> 1] = pack_bf16(p0, p1);
+                }
+                l += sum0 + sum1;
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {
+                    uint8_t* dst = sP + (ch >> 3) * TILE_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&p_full[wg]);
+                if (++st == F_STAGES) {
+                    st = 0;
+                    ph ^= 1;
+                }
+                ++tile_n;
+            }
+            // ---- epilogue: O / l (or the V column mean on uniform rows) -> bf16 -> smem -> TMA store
+            mbar_wait(&o_full[wg], (tile_n - 1) & 1);
+            tc_fence_after();
+            const bool uniform = !(l > 0.f);
+            const float inv = uniform ? 0.f : 1.f / l;
+            const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + hh * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * q + e]) * inv;
+                    if (uniform) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = vm[hh * 32 + 8 * q + e];
+                    }
+                    const int ch = hh * 4 + q;
+                    *reinterpret_cast<bf16x8*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = float_to_bf16x8(v);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            named_bar_sync(1 + wg, 128);
+            if (row == 0) {
+                tma_store_3d(&tmO, sP, h * D, qt * BT, b);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            named_bar_sync(1 + wg, 128);
+            if (i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m + log2f(l));
+        }
+        if (row == 0) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================================
+// backward
+// =================================================================================================================
+constexpr int B_KV_STAGE = 2 * TILE_BYTES + 1024;         // K | V | ka[128] | ks[128]
+constexpr int B_OFF_KV = 0;                               // 2 stages (items)
+constexpr int B_OFF_QDO = 2 * B_KV_STAGE;                 // 2 stages x (Q | dO)
+constexpr int B_OFF_P = B_OFF_QDO + 4 * TILE_BYTES;       // [128 q x 128 k] bf16 in two 64-key halves
+constexpr int B_OFF_DS = B_OFF_P + 2 * TILE_BYTES;
+constexpr int B_OFF_STG = B_OFF_DS + 2 * TILE_BYTES;      // 16 KB staging: dQ half tiles (fp32), dK / dV tiles (bf16)
+constexpr int B_OFF_BAR = B_OFF_STG + TILE_BYTES;
+constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
+constexpr int B_THREADS = 512;
+constexpr int DQ_TILE_FLOATS = BT * D;
+
+struct BwdParams {
+    int B, L, Lp, n_q, n_kv, P, q_tiles, k_tiles, total;
+    const int* ka;
+    const int* ks;
+    const int* act;
+    const int* sess;
+    const float* lse;    // [B, n_q, L] log2 domain, +inf = uniform row
+    const float* dsum;   // [B, n_q, L]
+    const unsigned* uni_bits;  // [B]: bit qt = query tile qt holds a uniform row
+    float scale, scale_log2, inv_L;
+    float* dq_acc;       // [B, n_q, q_tiles][2 halves][128 rows][32 floats], 16-byte chunks XOR-swizzled by (row & 7)
+};
+
+template <int KIND>
+__device__ __forceinline__ void bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask) {
+    const int per = p.B * p.n_kv;
+    kt = w / per;  // key tile 0 meets the most query tiles: heaviest first
+    const int rem = w % per;
+    b = rem / p.n_kv;
+    g = rem % p.n_kv;
+    const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
+    if (kind_causal<KIND>()) qmask = ((all >> kt) << kt) | (p.uni_bits[b] & all);
+    else qmask = all;
+}
+// step n of an item -> (head within the group, query tile): head-major, query tiles ascending
+__device__ __forceinline__ void bwd_step(unsigned qmask, int n_per_head, int n, int& hh, int& qt) {
+    hh = n >= n_per_head ? 1 : 0;
+    const int k = n - hh * n_per_head;
+    unsigned m = qmask;
+    for (int x = 0; x < k; ++x) m &= m - 1;
+    qt = __ffs(m) - 1;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(B_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV, BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+    uint64_t* kv_full = bars + 0;    // [2]
+    uint64_t* kv_free = bars + 2;    // [2]
+    uint64_t* qdo_full = bars + 4;   // [2]
+    uint64_t* qdo_free = bars + 6;   // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_free = bars + 9;
+    uint64_t* dp_full = bars + 10;
+    uint64_t* pds_full = bars + 11;
+    uint64_t* p_free = bars + 12;
+    uint64_t* ds_free = bars + 13;
+    uint64_t* dq_full = bars + 14;
+    uint64_t* dq_free = bars + 15;
+    uint64_t* dkv_full = bars + 16;
+    uint64_t* dkv_free = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmQ);
+        prefetch_tmap(&tmK);
+        prefetch_tmap(&tmV);
+        prefetch_tmap(&tmdO);
+        prefetch_tmap(&tmdK);
+        prefetch_tmap(&tmdV);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_free[s], 1);
+            mbar_init(&qdo_full[s], 1);
+            mbar_init(&qdo_free[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
+        mbar_init(dp_full, 1);
+        mbar_init(pds_full, 256);
+        mbar_init(p_free, 1);
+        mbar_init(ds_free, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_free, 128);
+        mbar_init(dkv_full, 1);
+        mbar_init(dkv_free, 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+    constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t item_n = 0, step_n = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+                int b, g, kt;
+                unsigned qmask;
+                bwd_decode<KIND>(w, p, b, g, kt, qmask);
+                const int nph = __popc(qmask), N = 2 * nph;
+                const int ks = item_n & 1;
+                uint8_t* skv = smem + B_OFF_KV + ks * B_KV_STAGE;
+                mbar_wait(&kv_free[ks], ((item_n >> 1) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[ks], B_KV_STAGE);
+                tma_load_3d(skv, &tmK, &kv_full[ks], g * D, kt * BT, b);
+                tma_load_3d(skv + TILE_BYTES, &tmV, &kv_full[ks], g * D, kt * BT, b);
+                bulk_load_1d(skv + 2 * TILE_BYTES, p.ka + (long long)b * p.Lp + kt * BT, 512, &kv_full[ks]);
+                bulk_load_1d(skv + 2 * TILE_BYTES + 512, p.ks + (long long)b * p.Lp + kt * BT, 512, &kv_full[ks]);
+                for (int n = 0; n < N; ++n, ++step_n) {
+                    int hh, qt;
+                    bwd_step(qmask, nph, n, hh, qt);
+                    const int st = step_n & 1;
+                    mbar_wait(&qdo_free[st], ((step_n >> 1) & 1) ^ 1);
+                    uint8_t* sq = smem + B_OFF_QDO + st * 2 * TILE_BYTES;
+                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
+                    tma_load_3d(sq, &tmQ, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
+                    tma_load_3d(sq + TILE_BYTES, &tmdO, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t item_n = 0, step_n = 0;
+            const uint32_t sp = smem_u32(smem + B_OFF_P), sds = smem_u32(smem + B_OFF_DS);
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+                int b, g, kt;
+                unsigned qmask;
+                bwd_decode<KIND>(w, p, b, g, kt, qmask);
+                const int N = 2 * __popc(qmask);
+                const int ks = item_n & 1;
+                const uint32_t sk = smem_u32(smem + B_OFF_KV + ks * B_KV_STAGE), sv = sk + TILE_BYTES;
+                mbar_wait(&kv_full[ks], (item_n >> 1) & 1);
+                {
+                    const int st = step_n & 1;
+                    mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                    if (step_n > 0) mbar_wait(s_free, (step_n - 1) & 1);  // S read by the previous item's last step
+                    tc_fence_after();
+                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * 2 * TILE_BYTES);
+                    issue_nt_128x128x64(tmem_base + T_S, sq, sk);
+                    umma_commit(s_full);
+                    // dP is free: the previous step's pds_full (waited on below) follows its last dP read
+                    issue_nt_128x128x64(tmem_base + T_DP, sq + TILE_BYTES, sv);
+                    umma_commit(dp_full);
+                }
+                for (int n = 0; n < N; ++n, ++step_n) {
+                    const int st = step_n & 1;
+                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * 2 * TILE_BYTES);
+                    const uint32_t sqn = smem_u32(smem + B_OFF_QDO + (st ^ 1) * 2 * TILE_BYTES);
+                    if (n + 1 < N) {
+                        mbar_wait(&qdo_full[st ^ 1], ((step_n + 1) >> 1) & 1);
+                        mbar_wait(s_free, step_n & 1);
+                        tc_fence_after();
+                        issue_nt_128x128x64(tmem_base + T_S, sqn, sk);
+                        umma_commit(s_full);
+                    }
+                    mbar_wait(pds_full, step_n & 1);
+                    if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
+                    tc_fence_after();
+                    issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0);   // dV += P^T dO
+                    umma_commit(p_free);
+                    issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0);               // dK += dS^T Q
+                    if (step_n > 0) {
+                        mbar_wait(dq_free, (step_n - 1) & 1);
+                        tc_fence_after();
+                    }
+                    issue_nn_128x64x128(tmem_base + T_DQ, sds, sk, false);               // dQ = dS K
+                    umma_commit(dq_full);
+                    umma_commit(ds_free);
+                    umma_commit(&qdo_free[st]);
+                    if (n + 1 < N) {
+                        issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv);     // dP(n+1) = dO V^T
+                        umma_commit(dp_full);
+                    } else {
+                        umma_commit(dkv_full);
+                        umma_commit(&kv_free[ks]);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== softmax / dS warps: warps 4-7 = key columns 0-63, 8-11 = 64-127 =====================
+        const int wg = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_off + T_S + wg * 64;
+        const uint32_t t_dp = tmem_base + lane_off + T_DP + wg * 64;
+        uint8_t* sP = smem + B_OFF_P + wg * TILE_BYTES;
+        uint8_t* sDS = smem + B_OFF_DS + wg * TILE_BYTES;
+        uint32_t item_n = 0, step_n = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask;
+            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            const int nph = __popc(qmask), N = 2 * nph;
+            const int ks = item_n & 1;
+            mbar_wait(&kv_full[ks], (item_n >> 1) & 1);  // key codes
+            const int4* mk4 = reinterpret_cast<const int4*>(smem + B_OFF_KV + ks * B_KV_STAGE + 2 * TILE_BYTES) + wg * 16;
+            const int jbase = kt * BT + wg * 64;
+            for (int n = 0; n < N; ++n, ++step_n) {
+                int hh, qt;
+                bwd_step(qmask, nph, n, hh, qt);
+                const int h = 2 * g + hh;
+                const int i = qt * BT + row;
+                float lse_i = INFINITY, dsum_i = 0.f;
+                int act_i = 0, sess_i = 0;
+                bool uni = false;
+                if (i < p.L) {
+                    const long long li = ((long long)b * p.n_q + h) * p.L + i;
+                    lse_i = p.lse[li];
+                    dsum_i = p.dsum[li];
+                    uni = (lse_i == INFINITY);
+                    if (kind_uses_act<KIND>()) act_i = p.act[(long long)b * p.L + i];
+                    if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
+                }
+                const int istart = (i / p.P) * p.P;
+                const bool diag = kind_causal<KIND>() && (qt == kt);
+                const bool above = kind_causal<KIND>() && (qt < kt);  // only uniform rows reach keys above the diagonal
+                mbar_wait(s_full, step_n & 1);
+                tc_fence_after();
+                uint32_t s[64];
+                tmem_ld_32x32(t_s, s);
+                tmem_ld_32x32(t_s + 32, s + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(s_free);
+                // ---- P
+#pragma unroll
+                for (int c4 = 0; c4 < 16; ++c4) {
+                    int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
+                    if (KIND != MASK_SESSION) a4 = mk4[c4];
+                    if (kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
+                    const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+                    const int sv4[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = c4 * 4 + e;
+                        const int cc = wg * 64 + c;  // key column within the 128-key tile
+                        const int j = jbase + c;
+                        bool ok;
+                        if (above) ok = false;
+                        else if (diag) ok = allow_tc<KIND, true>(av[e], sv4[e], act_i, sess_i, cc, row, j, i, istart);
+                        else ok = allow_tc<KIND, false>(av[e], sv4[e], act_i, sess_i, cc, row, j, i, istart);
+                        float pv = ok ? ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse_i)) : 0.f;
+                        if (uni) pv = (j < p.L) ? p.inv_L : 0.f;
+                        s[c] = __float_as_uint(pv);
+                    }
+                }
+                if (step_n > 0) mbar_wait(p_free, (step_n - 1) & 1);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint4 v;
+                    v.x = pack_bf16(__uint_as_float(s[8 * ch]), __uint_as_float(s[8 * ch + 1]));
+                    v.y = pack_bf16(__uint_as_float(s[8 * ch + 2]), __uint_as_float(s[8 * ch + 3]));
+                    v.z = pack_bf16(__uint_as_float(s[8 * ch + 4]), __uint_as_float(s[8 * ch + 5]));
+                    v.w = pack_bf16(__uint_as_float(s[8 * ch + 6]), __uint_as_float(s[8 * ch + 7]));
+                    *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+                }
+                // ---- dS = P o (dP - dsum)
+                mbar_wait(dp_full, step_n & 1);
+                tc_fence_after();
+                if (step_n > 0) mbar_wait(ds_free, (step_n - 1) & 1);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t dp[32];
+                    tmem_ld_32x32(t_dp + half * 32, dp);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = half * 32 + q * 8 + 2 * e;
+                            const float d0 = __uint_as_float(s[c]) * (__uint_as_float(dp[q * 8 + 2 * e]) - dsum_i);
+                            const float d1 = __uint_as_float(s[c + 1]) * (__uint_as_float(dp[q * 8 + 2 * e + 1]) - dsum_i);
+                            pk[e] = pack_bf16(d0, d1);
+                        }
+                        const int ch = half * 4 + q;
+                        *reinterpret_cast<uint4*>(sDS + row * 128 + ((ch ^ (row & 7)) << 4)) =
+                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(pds_full);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===================== drain warps: dQ tiles -> TMA fp32 reduce-add; dK / dV -> bf16 TMA store ================
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const uint32_t t_dq = tmem_base + lane_off + T_DQ;
+        uint8_t* stg = smem + B_OFF_STG;
+        uint32_t item_n = 0, step_n = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask;
+            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            const int nph = __popc(qmask), N = 2 * nph;
+            for (int n = 0; n < N; ++n, ++step_n) {
+                int hh, qt;
+                bwd_step(qmask, nph, n, hh, qt);
+                mbar_wait(dq_full, step_n & 1);
+                tc_fence_after();
+                uint32_t o[64];
+                tmem_ld_32x32(t_dq, o);
+                tmem_ld_32x32(t_dq + 32, o + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(dq_free);
+                float* dst = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (row == 0) bulk_wait_read0();  // the previous bulk op has finished reading the staging buffer
+                    named_bar_sync(3, 128);
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const int k = half * 32 + 4 * ch;
+                        const float4 v = make_float4(__uint_as_float(o[k]) * p.scale, __uint_as_float(o[k + 1]) * p.scale,
+                                                     __uint_as_float(o[k + 2]) * p.scale, __uint_as_float(o[k + 3]) * p.scale);
+                        *reinterpret_cast<float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(3, 128);
+                    if (row == 0) {
+                        bulk_reduce_add_f32(dst + half * (DQ_TILE_FLOATS / 2), stg, DQ_TILE_FLOATS * 2);
+                        bulk_commit();
+                    }
+                }
+            }
+            // ---- item epilogue: dK then dV -> bf16 -> staging -> TMA store (rows past L are clipped)
+            mbar_wait(dkv_full, item_n & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                const uint32_t t_acc = tmem_base + lane_off + (which == 0 ? T_DK : T_DV);
+                const float mul = (which == 0) ? p.scale : 1.f;
+                uint32_t o[64];
+                tmem_ld_32x32(t_acc, o);
+                tmem_ld_32x32(t_acc + 32, o + 32);
+                tmem_ld_wait();
+                if (which == 1) {
+                    tc_fence_before();
+                    mbar_arrive(dkv_free);
+                }
+                if (row == 0) bulk_wait_read0();
+                named_bar_sync(3, 128);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * ch + e]) * mul;
+                    *reinterpret_cast<bf16x8*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = float_to_bf16x8(v);
+                }
+                fence_proxy_async();
+                named_bar_sync(3, 128);
+                if (row == 0) {
+                    tma_store_3d(which == 0 ? &tmdK : &tmdV, stg, g * D, kt * BT, b);
+                    bulk_commit();
+                }
+            }
+        }
+        if (row == 0) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dsum[b,h,i] = sum_d dO*O ; uni_bits[b] |= 1 << (i / 128) for uniform rows (lse = +inf; head 0 decides: the mask is
+// head-independent)
+__global__ void attn_tc_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ld_o, int B,
+                                        int L, int n_q, const float* __restrict__ lse, float* __restrict__ dsum,
+                                        unsigned* __restrict__ uni_bits) {
+    const long long total = (long long)B * L * n_q;
+    const int sub = threadIdx.x & 7;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long gs = ((long long)gridDim.x * blockDim.x) >> 3;
+    const long long iters = (total + gs - 1) / gs;
+    for (long long it = 0; it < iters; ++it) {
+        const long long gi = g0 + it * gs;
+        const bool live = gi < total;
+        const long long row = live ? gi / n_q : 0;
+        const int h = live ? (int)(gi % n_q) : 0;
+        float a[8], d[8];
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8), a);
+        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8), d);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += a[i] * d[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (live && sub == 0) {
+            const int b = (int)(row / L), i = (int)(row % L);
+            const long long li = ((long long)b * n_q + h) * L + i;
+            dsum[li] = s;
+            if (h == 0 && lse[li] == INFINITY) atomicOr(&uni_bits[b], 1u << (i / BT));
+        }
+    }
+}
+
+// dq_acc (tile-major, swizzled fp32) -> dq bf16 [B*L, ld_d] + h*64.  One thread per 8 consecutive head-dim elements.
+__global__ void attn_tc_dq_convert_kernel(const float* __restrict__ acc, int B, int L, int n_q, int q_tiles,
+                                          bf16* __restrict__ dq, long long ld_d) {
+    const long long total = (long long)B * n_q * L * 8;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(x & 7);
+        long long r = x >> 3;
+        const int h = (int)(r % n_q);
+        r /= n_q;
+        const int i = (int)(r % L), b = (int)(r / L);
+        const int qt = i >> 7, row = i & 127;
+        const float* tile = acc + (((long long)b * n_q + h) * q_tiles + qt) * DQ_TILE_FLOATS + (c8 >> 2) * (DQ_TILE_FLOATS / 2) +
+                            row * 32;
+        const int ch = (c8 & 3) * 2;
+        const float4 v0 = *reinterpret_cast<const float4*>(tile + ((ch ^ (row & 7)) << 2));
+        const float4 v1 = *reinterpret_cast<const float4*>(tile + (((ch + 1) ^ (row & 7)) << 2));
+        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        *reinterpret_cast<bf16x8*>(dq + ((long long)b * L + i) * ld_d + h * D + c8 * 8) = float_to_bf16x8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 [B][L][cols] view (row stride ld elements, sequence stride L*ld); box = [1][128 rows][64 cols], SWIZZLE_128B
+int make_tmap_seq(CUtensorMap* m, const void* base, int B, int L, int cols, long long ld) {
+    EncodeTiledFn fn = encode_fn();
+    GAMER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    GAMER_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+                  "attention operands must be 16-byte aligned (ld=%lld)", ld);
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (attention) failed with %d (B=%d L=%d cols=%d ld=%lld)", (int)r, B,
+                  L, cols, ld);
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+inline long long align256(long long x) { return (x + 255) / 256 * 256; }
+
+struct MetaLayout {
+    int Lp, k_tiles;
+    long long off_ka, off_ks, off_flag, bytes;
+};
+MetaLayout meta_layout(int B, int L) {
+    MetaLayout m;
+    m.k_tiles = (L + BT - 1) / BT;
+    m.Lp = m.k_tiles * BT;
+    m.off_ka = 0;
+    m.off_ks = align256((long long)B * m.Lp * 4);
+    m.off_flag = m.off_ks + align256((long long)B * m.Lp * 4);
+    m.bytes = m.off_flag + align256((long long)B * m.k_tiles * 4);
+    return m;
+}
+
+int build_meta(int kind, const int* am, const int* act, const int* sess, int B, int L, uint8_t* ws, const MetaLayout& ml,
+               cudaStream_t stream) {
+    const int* act_in = (kind == MASK_MULTI_CROSS || kind == MASK_SESSION_CROSS) ? act : nullptr;
+    const int* sess_in = (kind == MASK_SESSION || kind == MASK_SESSION_CROSS) ? sess : nullptr;
+    attn_meta_kernel<<<B * ml.k_tiles, BT, 0, stream>>>(am, act_in, sess_in, L, ml.Lp, ml.k_tiles,
+                                                        reinterpret_cast<int*>(ws + ml.off_ka),
+                                                        reinterpret_cast<int*>(ws + ml.off_ks),
+                                                        reinterpret_cast<int*>(ws + ml.off_flag));
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
+int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+               const FwdParams& p, cudaStream_t stream) {
+    static bool cfg = false;
+    if (!cfg) {
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+        cfg = true;
+    }
+    const int grid = p.total < sm_count() ? p.total : sm_count();
+    attn_tc_fwd_kernel<KIND><<<grid, F_THREADS, F_SMEM, stream>>>(tq, tk, tv, to, p);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
+int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+               const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
+    static bool cfg = false;
+    if (!cfg) {
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        cfg = true;
+    }
+    const int grid = p.total < sm_count() ? p.total : sm_count();
+    attn_tc_bwd_kernel<KIND><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+bool attn_tc_supported(int L, int n_q, int n_kv, int head_dim) {
+    return head_dim == D && n_kv > 0 && n_q == 2 * n_kv && L >= 1 && (L + BT - 1) / BT <= 32;
+}
+
+long long attn_tc_fwd_ws_bytes(int B, int L) { return meta_layout(B, L).bytes; }
+
+int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv, int kind, int P,
+                const int* am, const int* act, const int* sess, float scale, const float* vmean, void* ws, void* o,
+                long long ld_o, float* lse, cudaStream_t stream) {
+    const MetaLayout ml = meta_layout(B, L);
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    if (int e = build_meta(kind, am, act, sess, B, L, w8, ml, stream)) return e;
+    CUtensorMap tq, tk, tv, to;
+    if (int e = make_tmap_seq(&tq, q, B, L, n_q * D, ld)) return e;
+    if (int e = make_tmap_seq(&tk, k, B, L, n_kv * D, ld)) return e;
+    if (int e = make_tmap_seq(&tv, v, B, L, n_kv * D, ld)) return e;
+    if (int e = make_tmap_seq(&to, o, B, L, n_q * D, ld_o)) return e;
+    FwdParams p{};
+    p.B = B; p.L = L; p.Lp = ml.Lp; p.n_q = n_q; p.n_kv = n_kv; p.P = P;
+    p.q_tiles = ml.k_tiles; p.k_tiles = ml.k_tiles; p.total = B * n_kv * ml.k_tiles;
+    p.ka = reinterpret_cast<const int*>(w8 + ml.off_ka);
+    p.ks = reinterpret_cast<const int*>(w8 + ml.off_ks);
+    p.tflag = reinterpret_cast<const int*>(w8 + ml.off_flag);
+    p.act = act; p.sess = sess; p.scale_log2 = scale * 1.4426950408889634f; p.vmean = vmean; p.lse = lse;
+    switch (kind) {
+        case 0: return launch_fwd<0>(tq, tk, tv, to, p, stream);
+        case 1: return launch_fwd<1>(tq, tk, tv, to, p, stream);
+        case 2: return launch_fwd<2>(tq, tk, tv, to, p, stream);
+        default: return launch_fwd<3>(tq, tk, tv, to, p, stream);
+    }
+}
+
+struct BwdLayout {
+    MetaLayout ml;
+    long long off_dsum, off_uni, off_acc, acc_bytes, bytes;
+};
+static BwdLayout bwd_layout(int B, int L, int n_q) {
+    BwdLayout bl;
+    bl.ml = meta_layout(B, L);
+    bl.off_dsum = bl.ml.bytes;
+    bl.off_uni = bl.off_dsum + align256((long long)B * n_q * L * 4);
+    bl.off_acc = bl.off_uni + align256((long long)B * 4);
+    bl.acc_bytes = (long long)B * n_q * bl.ml.k_tiles * DQ_TILE_FLOATS * 4;
+    bl.bytes = bl.off_acc + align256(bl.acc_bytes);
+    return bl;
+}
+
+long long attn_tc_bwd_ws_bytes(int B, int L, int n_q) { return bwd_layout(B, L, n_q).bytes; }
+
+int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv, int kind, int P,
+                const int* am, const int* act, const int* sess, float scale, const void* o, const void* d_o, long long ld_o,
+                const float* lse, void* ws, void* dq, void* dk, void* dv, long long ld_d, cudaStream_t stream) {
+    const BwdLayout bl = bwd_layout(B, L, n_q);
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    if (int e = build_meta(kind, am, act, sess, B, L, w8, bl.ml, stream)) return e;
+    float* dsum = reinterpret_cast<float*>(w8 + bl.off_dsum);
+    unsigned* uni = reinterpret_cast<unsigned*>(w8 + bl.off_uni);
+    float* acc = reinterpret_cast<float*>(w8 + bl.off_acc);
+    // uni bits and the dQ accumulator are adjacent: one memset
+    GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)(bl.off_acc - bl.off_uni) + (size_t)bl.acc_bytes, stream));
+    {
+        const long long groups = (long long)B * L * n_q;
+        const long long blocks = (groups * 8 + 255) / 256;
+        attn_tc_bwd_prep_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(
+            reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), ld_o, B, L, n_q, lse, dsum, uni);
+        GAMER_LAUNCH_CHECK();
+    }
+    CUtensorMap tq, tk, tv, tdo, tdk, tdv;
+    if (int e = make_tmap_seq(&tq, q, B, L, n_q * D, ld)) return e;
+    if (int e = make_tmap_seq(&tk, k, B, L, n_kv * D, ld)) return e;
+    if (int e = make_tmap_seq(&tv, v, B, L, n_kv * D, ld)) return e;
+    if (int e = make_tmap_seq(&tdo, d_o, B, L, n_q * D, ld_o)) return e;
+    if (int e = make_tmap_seq(&tdk, dk, B, L, n_kv * D, ld_d)) return e;
+    if (int e = make_tmap_seq(&tdv, dv, B, L, n_kv * D, ld_d)) return e;
+    BwdParams p{};
+    p.B = B; p.L = L; p.Lp = bl.ml.Lp; p.n_q = n_q; p.n_kv = n_kv; p.P = P;
+    p.q_tiles = bl.ml.k_tiles; p.k_tiles = bl.ml.k_tiles; p.total = B * n_kv * bl.ml.k_tiles;
+    p.ka = reinterpret_cast<const int*>(w8 + bl.ml.off_ka);
+    p.ks = reinterpret_cast<const int*>(w8 + bl.ml.off_ks);
+    p.act = act; p.sess = sess; p.lse = lse; p.dsum = dsum; p.uni_bits = uni;
+    p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.inv_L = 1.0f / (float)L; p.dq_acc = acc;
+    int e;
+    switch (kind) {
+        case 0: e = launch_bwd<0>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        case 1: e = launch_bwd<1>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        case 2: e = launch_bwd<2>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        default: e = launch_bwd<3>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+    }
+    if (e) return e;
+    {
+        const long long total = (long long)B * n_q * L * 8;
+        const long long blocks = (total + 255) / 256;
+        attn_tc_dq_convert_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+            acc, B, L, n_q, bl.ml.k_tiles, reinterpret_cast<bf16*>(dq), ld_d);
+        GAMER_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -162,7 +162,7 @@ def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
     call("gamer_attn_fwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
          float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _stream(),
          work=(4 * hd * n_q * B * L * (L + 1) // 2, B * L * (2 * n_q + 2 * n_kv) * hd * 2))   # causal pair count (§8d)
-    return o, lse, ws.view(torch.float32).view(B, n_kv, hd)
+    return o, lse, ws[: B * n_kv * hd * 4].view(torch.float32).view(B, n_kv, hd)
 
 
 def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv):

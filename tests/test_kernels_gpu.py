@@ -340,7 +340,7 @@ def _attn_inputs(B, L, seed, left_pad):
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
-@pytest.mark.parametrize("L,left_pad", [(65, False), (200, True), (37, False)])
+@pytest.mark.parametrize("L,left_pad", [(65, False), (200, True), (37, False), (505, False), (256, True), (129, False)])
 def test_attention_fwd_bwd(kind, L, left_pad):
     from oracle import oracle_model as om
     k = _k()
