@@ -27,6 +27,20 @@ constexpr int BT = 128;               // tile edge: queries and keys
 constexpr int TILE_BYTES = BT * D * 2;  // 16 KB: one [128 x 64] bf16 SWIZZLE_128B tile
 constexpr int KC_MAX = 0x7fffffff;
 
+// Optional in-kernel timeline (debug hook gamer_attn_set_trace): CTA 0 appends (tag, clock64) pairs.
+struct Trace {
+    long long* buf;
+    int cap;
+};
+__device__ __forceinline__ void trace_pt(const Trace& tr, int role, int& n, int tag) {
+    if (tr.buf != nullptr && blockIdx.x == 0 && n < tr.cap) {
+        tr.buf[(role * tr.cap + n) * 2] = tag;
+        tr.buf[(role * tr.cap + n) * 2 + 1] = clock64();
+        ++n;
+    }
+}
+Trace g_trace = {nullptr, 0};
+
 template <int KIND>
 __host__ __device__ constexpr bool kind_causal() { return KIND == MASK_CAUSAL || KIND == MASK_MULTI_CROSS; }
 template <int KIND>
@@ -40,21 +54,25 @@ __host__ __device__ constexpr bool kind_uses_sess() { return KIND == MASK_SESSIO
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void attn_meta_kernel(const int* __restrict__ am, const int* __restrict__ act, const int* __restrict__ sess,
                                  int L, int Lp, int k_tiles, int* __restrict__ ka, int* __restrict__ ks,
-                                 int* __restrict__ tflag) {
+                                 int* __restrict__ qa, int* __restrict__ qs, int* __restrict__ tflag) {
     const int b = blockIdx.x / k_tiles, t = blockIdx.x % k_tiles;
     const int j = t * BT + threadIdx.x;
     bool valid = false;
-    int a = KC_MAX, s = KC_MAX;
+    int a = KC_MAX, s = KC_MAX, a_raw = 0, s_raw = 0;
     if (j < L) {
         const long long idx = (long long)b * L + j;
         valid = am[idx] != 0;
+        a_raw = act ? act[idx] : 0;
+        s_raw = sess ? sess[idx] : 0;
         if (valid) {
-            a = act ? act[idx] : 0;
-            s = sess ? sess[idx] : 0;
+            a = a_raw;
+            s = s_raw;
         }
     }
     ka[(long long)b * Lp + j] = a;
     ks[(long long)b * Lp + j] = s;
+    qa[(long long)b * Lp + j] = a_raw;  // query side: the predicate does not look at the query's own padding bit
+    qs[(long long)b * Lp + j] = s_raw;
     const int all = __syncthreads_and(valid ? 1 : 0);
     if (threadIdx.x == 0) tflag[blockIdx.x] = all;
 }
@@ -102,17 +120,14 @@ __device__ __forceinline__ void issue_tn_128x64x128(uint32_t d_tmem, uint32_t sa
                   (acc || k != 0) ? 1u : 0u);
 }
 
-// cold path of the online softmax: multiply this thread's O row (64 fp32 TMEM columns) by alpha
+// cold path of the online softmax: multiply this thread's 32 fp32 TMEM columns of an O row by alpha
 __device__ __noinline__ void rescale_o_row(uint32_t t_o, float alpha) {
-#pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
-        uint32_t o[32];
-        tmem_ld_32x32(t_o + hh * 32, o);
-        tmem_ld_wait();
+    uint32_t o[32];
+    tmem_ld_32x32(t_o, o);
+    tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-        tmem_st_32x32(t_o + hh * 32, o);
-    }
+    for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+    tmem_st_32x32(t_o, o);
     tmem_st_wait();
 }
 
@@ -126,8 +141,9 @@ constexpr int F_OFF_Q = 0;                                     // 2 heads
 constexpr int F_OFF_KV = 2 * TILE_BYTES;
 constexpr int F_OFF_P = F_OFF_KV + F_STAGES * F_STAGE_BYTES;   // 2 heads x 2 halves
 constexpr int F_OFF_BAR = F_OFF_P + 4 * TILE_BYTES;
-constexpr int F_SMEM = F_OFF_BAR + 256 + 1024;
-constexpr int F_THREADS = 384;
+constexpr int F_OFF_X = F_OFF_BAR + 256;                      // row max / row sum exchange: [2 heads][2][2][128] fp32
+constexpr int F_SMEM = F_OFF_X + 4096 + 1024;
+constexpr int F_THREADS = 640;
 
 struct FwdParams {
     int B, L, Lp, n_q, n_kv, P, q_tiles, k_tiles, total;
@@ -139,6 +155,7 @@ struct FwdParams {
     float scale_log2;
     const float* vmean;
     float* lse;
+    Trace tr;
 };
 
 template <int KIND>
@@ -151,28 +168,30 @@ __device__ __forceinline__ void fwd_decode(int w, const FwdParams& p, int& b, in
     T = kind_causal<KIND>() ? min(qt + 1, p.k_tiles) : p.k_tiles;
 }
 
-// mask + row max over the 128 scores of one tile held in registers
-template <int KIND, bool DIAG>
-__device__ __forceinline__ float mask_max(uint32_t (&s)[128], const int4* mk4, int act_i, int sess_i, int row, int j0, int i,
-                                          int istart) {
-    float mx = -INFINITY;
+// mask + partial row max over this thread's 64 scores of a tile (4 independent max chains).  `cc0` = first key column of
+// the thread's half within the 128-key tile.  CODES = false: the tile's keys are all valid and the kind is CAUSAL, so
+// only the diagonal test remains.
+template <int KIND, bool DIAG, bool CODES>
+__device__ __forceinline__ float mask_max(uint32_t (&s)[64], const int4* mk4, int act_i, int sess_i, int cc0, int row, int j0,
+                                          int i, int istart) {
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int c4 = 0; c4 < 32; ++c4) {
+    for (int c4 = 0; c4 < 16; ++c4) {
         int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
-        if (KIND != MASK_SESSION) a4 = mk4[c4];
-        if (kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
+        if (CODES && KIND != MASK_SESSION) a4 = mk4[c4];
+        if (CODES && kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
         const int av[4] = {a4.x, a4.y, a4.z, a4.w};
         const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            const bool ok = allow_tc<KIND, DIAG>(av[e], sv[e], act_i, sess_i, c, row, j0 + c, i, istart);
+            const bool ok = allow_tc<KIND, DIAG>(av[e], sv[e], act_i, sess_i, cc0 + c, row, j0 + c, i, istart);
             const float v = ok ? __uint_as_float(s[c]) : -INFINITY;
             s[c] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
+            mx[e] = fmaxf(mx[e], v);
         }
     }
-    return mx;
+    return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
 }
 
 template <int KIND>
@@ -205,7 +224,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         for (int h = 0; h < 2; ++h) {
             mbar_init(&s_full[h], 1);
-            mbar_init(&p_full[h], 128);
+            mbar_init(&p_full[h], 256);
             mbar_init(&o_full[h], 1);
         }
         fence_barrier_init();
@@ -248,7 +267,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            int st = 0;
+            int st = 0, tn = 0;
             uint32_t ph = 0, item_par = 0, tile_n = 0;
             const uint32_t sq = smem_u32(smem + F_OFF_Q);
             const uint32_t sp = smem_u32(smem + F_OFF_P);
@@ -256,8 +275,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 int b, g, qt, T;
                 fwd_decode<KIND>(w, p, b, g, qt, T);
                 mbar_wait(q_full, item_par);
+                trace_pt(p.tr, 0, tn, 1);
                 mbar_wait(&kv_full[st], ph);
                 tc_fence_after();
+                trace_pt(p.tr, 0, tn, 2);
                 {
                     const uint32_t sk = smem_u32(smem + F_OFF_KV + st * F_STAGE_BYTES);
                     issue_nt_128x128x64(tmem_base + 0, sq, sk);
@@ -279,6 +300,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&p_full[h], tile_n & 1);
                         tc_fence_after();
+                        trace_pt(p.tr, 0, tn, 10 + h);
                         if (t + 1 < T) {
                             if (h == 0) {
                                 mbar_wait(&kv_full[nst], nph);
@@ -300,19 +322,28 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ===================== softmax warpgroups: warps 4-7 = head A, 8-11 = head B =====================
-        const int wg = (warp - 4) >> 2;
+        // ===================== softmax: 16 warps.  warps 4-11 = head A, 12-19 = head B; within a head the first four
+        // warps take key columns 0-63 of the tile, the other four 64-127 (one query row per thread, row max exchanged
+        // through shared memory) =====================
+        const int hd = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;
         const int wq = warp & 3;  // TMEM lane quarter of this warp
         const int row = wq * 32 + lane;
-        const uint32_t t_s = tmem_base + ((uint32_t)(wq * 32) << 16) + wg * 128;
-        const uint32_t t_o = tmem_base + ((uint32_t)(wq * 32) << 16) + 256 + wg * 64;
-        uint8_t* sP = smem + F_OFF_P + wg * 2 * TILE_BYTES;
-        int st = 0;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_off + hd * 128 + half * 64;
+        const uint32_t t_o = tmem_base + lane_off + 256 + hd * 64 + half * 32;
+        uint8_t* sStage = smem + F_OFF_P + hd * 2 * TILE_BYTES;          // O staging = this head's first P half buffer
+        const uint32_t sPh = smem_u32(sStage + half * TILE_BYTES);        // the P half this thread writes
+        float* xchg = reinterpret_cast<float*>(smem + F_OFF_X) + hd * 512;  // [2 buffers][2 halves][128 rows]
+        const int bar_id = 1 + hd;
+        int st = 0, tn = 0;
         uint32_t ph = 0, tile_n = 0;
+        Trace tr = p.tr;
+        if (row != 0 || half != 0) tr.buf = nullptr;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
             int b, g, qt, T;
             fwd_decode<KIND>(w, p, b, g, qt, T);
-            const int h = 2 * g + wg;
+            const int h = 2 * g + hd;
             const int i = qt * BT + row;
             int act_i = 0, sess_i = 0;
             if (i < p.L) {
@@ -320,62 +351,78 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
             }
             const int istart = (i / p.P) * p.P;
+            unsigned allvalid = 0;  // bit t: every key of tile t is valid (CAUSAL tiles below the diagonal then need no mask)
+            if (KIND == MASK_CAUSAL) {
+                for (int t = 0; t < T; ++t) allvalid |= (p.tflag[b * p.k_tiles + t] != 0 ? 1u : 0u) << t;
+            }
             float m = -INFINITY, l = 0.f;
             for (int t = 0; t < T; ++t) {
-                const int* meta = reinterpret_cast<const int*>(smem + F_OFF_KV + st * F_STAGE_BYTES + 2 * TILE_BYTES);
-                bool need_mask = true;
+                const int4* mk4 =
+                    reinterpret_cast<const int4*>(smem + F_OFF_KV + st * F_STAGE_BYTES + 2 * TILE_BYTES) + half * 16;
                 const bool diag = kind_causal<KIND>() && (t == qt);
-                if (KIND == MASK_CAUSAL) need_mask = diag || (p.tflag[b * p.k_tiles + t] == 0);
+                const bool codes = (KIND != MASK_CAUSAL) || (((allvalid >> t) & 1u) == 0);
                 mbar_wait(&kv_full[st], ph);  // key codes of this stage (already complete: the S MMA waited on it)
-                mbar_wait(&s_full[wg], tile_n & 1);
+                trace_pt(tr, 1 + hd, tn, 20);
+                mbar_wait(&s_full[hd], tile_n & 1);
                 tc_fence_after();
-                uint32_t s[128];
+                trace_pt(tr, 1 + hd, tn, 21);
+                uint32_t s[64];
                 tmem_ld_32x32(t_s, s);
                 tmem_ld_32x32(t_s + 32, s + 32);
-                tmem_ld_32x32(t_s + 64, s + 64);
-                tmem_ld_32x32(t_s + 96, s + 96);
                 tmem_ld_wait();
-                float mx = -INFINITY;
-                if (need_mask) {
-                    const int4* mk4 = reinterpret_cast<const int4*>(meta);
-                    if (diag) mx = mask_max<KIND, true>(s, mk4, act_i, sess_i, row, t * BT, i, istart);
-                    else mx = mask_max<KIND, false>(s, mk4, act_i, sess_i, row, t * BT, i, istart);
+                trace_pt(tr, 1 + hd, tn, 22);
+                float mx;
+                const int j0 = t * BT + half * 64;
+                if (codes) {
+                    if (diag) mx = mask_max<KIND, true, true>(s, mk4, act_i, sess_i, half * 64, row, j0, i, istart);
+                    else mx = mask_max<KIND, false, true>(s, mk4, act_i, sess_i, half * 64, row, j0, i, istart);
+                } else if (diag) {
+                    mx = mask_max<KIND, true, false>(s, mk4, act_i, sess_i, half * 64, row, j0, i, istart);
                 } else {
+                    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                    for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+                    for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(s[c]));
+                    mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 }
+                // the other half of the row
+                float* xb = xchg + (tile_n & 1) * 256;
+                xb[half * 128 + row] = mx;
+                named_bar_sync(bar_id, 256);
+                mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
                 // lazy running max (log2 domain): raise it only from -inf or by more than 2^64
                 const float m_tile = mx * p.scale_log2;
                 float m_new = m;
                 if (m == -INFINITY) m_new = m_tile;
                 else if (m_tile > m + 64.f) m_new = m_tile;
                 const bool rescale = (m != -INFINITY) && (m_new != m);
+                trace_pt(tr, 1 + hd, tn, 23);
                 if (t > 0) {
-                    mbar_wait(&o_full[wg], (tile_n - 1) & 1);  // PV(t-1) done: O stable, P buffer free
+                    mbar_wait(&o_full[hd], (tile_n - 1) & 1);  // PV(t-1) done: O stable, P buffer free
                     tc_fence_after();
                     if (__any_sync(0xffffffffu, rescale)) rescale_o_row(t_o, rescale ? ex2_approx(m - m_new) : 1.f);
                 }
                 if (rescale) l *= ex2_approx(m - m_new);
+                trace_pt(tr, 1 + hd, tn, 24);
                 m = m_new;
                 const float neg_m = (m == -INFINITY) ? 0.f : -m;
-                float sum0 = 0.f, sum1 = 0.f;
+                float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int c = 0; c < 128; c += 2) {
+                for (int c = 0; c < 64; c += 2) {
                     const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
                     const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
-                    sum0 += p0;
-                    sum1 += p1;
+                    sum[(c >> 1) & 1] += p0;
+                    sum[2 + ((c >> 1) & 1)] += p1;
                     s[c >> 1] = pack_bf16(p0, p1);
                 }
-                l += sum0 + sum1;
+                l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+                trace_pt(tr, 1 + hd, tn, 25);
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
-                    uint8_t* dst = sP + (ch >> 3) * TILE_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
-                }
+                for (int ch = 0; ch < 8; ++ch)
+                    sts128(sPh + row * 128 + ((ch ^ (row & 7)) << 4), s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(&p_full[wg]);
+                mbar_arrive(&p_full[hd]);
+                trace_pt(tr, 1 + hd, tn, 26);
                 if (++st == F_STAGES) {
                     st = 0;
                     ph ^= 1;
@@ -383,15 +430,21 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 ++tile_n;
             }
             // ---- epilogue: O / l (or the V column mean on uniform rows) -> bf16 -> smem -> TMA store
-            mbar_wait(&o_full[wg], (tile_n - 1) & 1);
+            {
+                float* xb = xchg + (tile_n & 1) * 256;
+                xb[half * 128 + row] = l;
+                named_bar_sync(bar_id, 256);
+                l += xb[(half ^ 1) * 128 + row];
+            }
+            mbar_wait(&o_full[hd], (tile_n - 1) & 1);
             tc_fence_after();
+            trace_pt(tr, 1 + hd, tn, 30);
             const bool uniform = !(l > 0.f);
             const float inv = uniform ? 0.f : 1.f / l;
-            const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D + half * 32;
+            {
                 uint32_t o[32];
-                tmem_ld_32x32(t_o + hh * 32, o);
+                tmem_ld_32x32(t_o, o);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -400,24 +453,25 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * q + e]) * inv;
                     if (uniform) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = vm[hh * 32 + 8 * q + e];
+                        for (int e = 0; e < 8; ++e) v[e] = vm[8 * q + e];
                     }
-                    const int ch = hh * 4 + q;
-                    *reinterpret_cast<bf16x8*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = float_to_bf16x8(v);
+                    const int ch = half * 4 + q;
+                    *reinterpret_cast<bf16x8*>(sStage + row * 128 + ((ch ^ (row & 7)) << 4)) = float_to_bf16x8(v);
                 }
             }
             tc_fence_before();
             fence_proxy_async();
-            named_bar_sync(1 + wg, 128);
-            if (row == 0) {
-                tma_store_3d(&tmO, sP, h * D, qt * BT, b);
+            named_bar_sync(bar_id, 256);
+            if (row == 0 && half == 0) {
+                tma_store_3d(&tmO, sStage, h * D, qt * BT, b);
                 bulk_commit();
                 bulk_wait_read0();
             }
-            named_bar_sync(1 + wg, 128);
-            if (i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m + log2f(l));
+            named_bar_sync(bar_id, 256);
+            trace_pt(tr, 1 + hd, tn, 31);
+            if (half == 0 && i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m + log2f(l));
         }
-        if (row == 0) bulk_wait0();
+        if (row == 0 && half == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -429,26 +483,28 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =================================================================================================================
 constexpr int B_KV_STAGE = 2 * TILE_BYTES + 1024;         // K | V | ka[128] | ks[128]
 constexpr int B_OFF_KV = 0;                               // 2 stages (items)
-constexpr int B_OFF_QDO = 2 * B_KV_STAGE;                 // 2 stages x (Q | dO)
-constexpr int B_OFF_P = B_OFF_QDO + 4 * TILE_BYTES;       // [128 q x 128 k] bf16 in two 64-key halves
+constexpr int B_QDO_STAGE = 2 * TILE_BYTES + 2048;        // Q | dO | lse[128] | dsum[128] | level[128] | session[128]
+constexpr int B_OFF_QDO = 2 * B_KV_STAGE;                 // 2 stages
+constexpr int B_OFF_P = B_OFF_QDO + 2 * B_QDO_STAGE;      // [128 q x 128 k] bf16 in two 64-key halves
 constexpr int B_OFF_DS = B_OFF_P + 2 * TILE_BYTES;
 constexpr int B_OFF_STG = B_OFF_DS + 2 * TILE_BYTES;      // 16 KB staging: dQ half tiles (fp32), dK / dV tiles (bf16)
 constexpr int B_OFF_BAR = B_OFF_STG + TILE_BYTES;
 constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
-constexpr int B_THREADS = 512;
+constexpr int B_THREADS = 768;
 constexpr int DQ_TILE_FLOATS = BT * D;
 
 struct BwdParams {
     int B, L, Lp, n_q, n_kv, P, q_tiles, k_tiles, total;
     const int* ka;
     const int* ks;
-    const int* act;
-    const int* sess;
-    const float* lse;    // [B, n_q, L] log2 domain, +inf = uniform row
-    const float* dsum;   // [B, n_q, L]
+    const int* qa;
+    const int* qs;       // [B, Lp] query-side behaviour level / session (zero past L)
+    const float* lse_p;  // [B, n_q, Lp] log2 domain, +inf = uniform row or i >= L
+    const float* dsum_p; // [B, n_q, Lp]
     const unsigned* uni_bits;  // [B]: bit qt = query tile qt holds a uniform row
     float scale, scale_log2, inv_L;
     float* dq_acc;       // [B, n_q, q_tiles][2 halves][128 rows][32 floats], 16-byte chunks XOR-swizzled by (row & 7)
+    Trace tr;
 };
 
 template <int KIND>
@@ -469,6 +525,36 @@ __device__ __forceinline__ void bwd_step(unsigned qmask, int n_per_head, int n, 
     unsigned m = qmask;
     for (int x = 0; x < k; ++x) m &= m - 1;
     qt = __ffs(m) - 1;
+}
+
+// P = exp2(S * scale_log2 - lse) on allowed pairs, 0 elsewhere; uniform rows (lim_u > 0) get 1/L on every key column
+// c < lim_u.  Branch-free per element (the tile variant is a template parameter): MODE 0 = below the diagonal / non-causal,
+// 1 = diagonal tile, 2 = above the diagonal (only uniform rows are non-zero there).  `cc0` = first key column of this
+// thread's half within the 128-key tile.
+template <int KIND, int MODE>
+__device__ __forceinline__ void bwd_p_tile(uint32_t (&s)[32], const int4* mk4, int act_i, int sess_i, int cc0, int row,
+                                           int jbase, int i, int istart, float scale_log2, float lse_i, int lim_u,
+                                           float inv_L) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
+        if (MODE != 2 && KIND != MASK_SESSION) a4 = mk4[c4];
+        if (MODE != 2 && kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
+        const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const int sv4[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float pv = 0.f;
+            if (MODE != 2) {
+                const bool ok = allow_tc<KIND, MODE == 1>(av[e], sv4[e], act_i, sess_i, cc0 + c, row, jbase + c, i, istart);
+                const float x = fmaf(__uint_as_float(s[c]), scale_log2, -lse_i);
+                pv = ex2_approx(ok ? x : -INFINITY);
+            }
+            pv = (c < lim_u) ? inv_L : pv;
+            s[c] = __float_as_uint(pv);
+        }
+    }
 }
 
 template <int KIND>
@@ -510,9 +596,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_init(&qdo_free[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_free, 256);
+        mbar_init(s_free, 512);
         mbar_init(dp_full, 1);
-        mbar_init(pds_full, 256);
+        mbar_init(pds_full, 512);
         mbar_init(p_free, 1);
         mbar_init(ds_free, 1);
         mbar_init(dq_full, 1);
@@ -551,10 +637,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     bwd_step(qmask, nph, n, hh, qt);
                     const int st = step_n & 1;
                     mbar_wait(&qdo_free[st], ((step_n >> 1) & 1) ^ 1);
-                    uint8_t* sq = smem + B_OFF_QDO + st * 2 * TILE_BYTES;
-                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
+                    uint8_t* sq = smem + B_OFF_QDO + st * B_QDO_STAGE;
+                    mbar_expect_tx(&qdo_full[st], B_QDO_STAGE);
                     tma_load_3d(sq, &tmQ, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
                     tma_load_3d(sq + TILE_BYTES, &tmdO, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
+                    const long long ro = ((long long)b * p.n_q + 2 * g + hh) * p.Lp + qt * BT;
+                    bulk_load_1d(sq + 2 * TILE_BYTES, p.lse_p + ro, 512, &qdo_full[st]);
+                    bulk_load_1d(sq + 2 * TILE_BYTES + 512, p.dsum_p + ro, 512, &qdo_full[st]);
+                    bulk_load_1d(sq + 2 * TILE_BYTES + 1024, p.qa + (long long)b * p.Lp + qt * BT, 512, &qdo_full[st]);
+                    bulk_load_1d(sq + 2 * TILE_BYTES + 1536, p.qs + (long long)b * p.Lp + qt * BT, 512, &qdo_full[st]);
                 }
             }
         }
@@ -562,6 +653,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t item_n = 0, step_n = 0;
+            int tn = 0;
             const uint32_t sp = smem_u32(smem + B_OFF_P), sds = smem_u32(smem + B_OFF_DS);
             for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
                 int b, g, kt;
@@ -571,12 +663,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const int ks = item_n & 1;
                 const uint32_t sk = smem_u32(smem + B_OFF_KV + ks * B_KV_STAGE), sv = sk + TILE_BYTES;
                 mbar_wait(&kv_full[ks], (item_n >> 1) & 1);
+                trace_pt(p.tr, 0, tn, 1);
                 {
                     const int st = step_n & 1;
                     mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                    trace_pt(p.tr, 0, tn, 2);
                     if (step_n > 0) mbar_wait(s_free, (step_n - 1) & 1);  // S read by the previous item's last step
                     tc_fence_after();
-                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * 2 * TILE_BYTES);
+                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
                     issue_nt_128x128x64(tmem_base + T_S, sq, sk);
                     umma_commit(s_full);
                     // dP is free: the previous step's pds_full (waited on below) follows its last dP read
@@ -585,8 +679,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
                 for (int n = 0; n < N; ++n, ++step_n) {
                     const int st = step_n & 1;
-                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * 2 * TILE_BYTES);
-                    const uint32_t sqn = smem_u32(smem + B_OFF_QDO + (st ^ 1) * 2 * TILE_BYTES);
+                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
+                    const uint32_t sqn = smem_u32(smem + B_OFF_QDO + (st ^ 1) * B_QDO_STAGE);
                     if (n + 1 < N) {
                         mbar_wait(&qdo_full[st ^ 1], ((step_n + 1) >> 1) & 1);
                         mbar_wait(s_free, step_n & 1);
@@ -594,9 +688,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         issue_nt_128x128x64(tmem_base + T_S, sqn, sk);
                         umma_commit(s_full);
                     }
+                    trace_pt(p.tr, 0, tn, 3);
                     mbar_wait(pds_full, step_n & 1);
+                    trace_pt(p.tr, 0, tn, 4);
                     if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
                     tc_fence_after();
+                    if (n + 1 < N) {  // dP of the next step first: its buffer is free (pds_full follows the dP read)
+                        issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv);     // dP(n+1) = dO V^T
+                        umma_commit(dp_full);
+                    }
                     issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0);   // dV += P^T dO
                     umma_commit(p_free);
                     issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0);               // dK += dS^T Q
@@ -604,31 +704,35 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         mbar_wait(dq_free, (step_n - 1) & 1);
                         tc_fence_after();
                     }
+                    trace_pt(p.tr, 0, tn, 5);
                     issue_nn_128x64x128(tmem_base + T_DQ, sds, sk, false);               // dQ = dS K
                     umma_commit(dq_full);
                     umma_commit(ds_free);
                     umma_commit(&qdo_free[st]);
-                    if (n + 1 < N) {
-                        issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv);     // dP(n+1) = dO V^T
-                        umma_commit(dp_full);
-                    } else {
+                    if (n + 1 == N) {
                         umma_commit(dkv_full);
                         umma_commit(&kv_free[ks]);
                     }
                 }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ===================== softmax / dS warps: warps 4-7 = key columns 0-63, 8-11 = 64-127 =====================
-        const int wg = (warp - 4) >> 2;
+    } else if (warp >= 4 && warp < 20) {
+        // ===================== softmax / dS warps: 16 warps, warpgroup k (warps 4+4k..7+4k) owns key columns [32k, 32k+32)
+        // of the tile; one query row per thread =====================
+        const int wgi = (warp - 4) >> 2;
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_off + T_S + wg * 64;
-        const uint32_t t_dp = tmem_base + lane_off + T_DP + wg * 64;
-        uint8_t* sP = smem + B_OFF_P + wg * TILE_BYTES;
-        uint8_t* sDS = smem + B_OFF_DS + wg * TILE_BYTES;
+        const uint32_t t_s = tmem_base + lane_off + T_S + wgi * 32;
+        const uint32_t t_dp = tmem_base + lane_off + T_DP + wgi * 32;
+        // P / dS live as two 64-key halves; this thread writes 16-byte chunks [4 (wgi & 1), 4 (wgi & 1) + 4) of its row
+        const uint32_t sP = smem_u32(smem + B_OFF_P + (wgi >> 1) * TILE_BYTES) + row * 128;
+        const uint32_t sDS = smem_u32(smem + B_OFF_DS + (wgi >> 1) * TILE_BYTES) + row * 128;
+        const int ch0 = (wgi & 1) * 4;
         uint32_t item_n = 0, step_n = 0;
+        int tn = 0;
+        Trace tr = p.tr;
+        if (row != 0 || wgi != 0) tr.buf = nullptr;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
             int b, g, kt;
             unsigned qmask;
@@ -636,104 +740,97 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int nph = __popc(qmask), N = 2 * nph;
             const int ks = item_n & 1;
             mbar_wait(&kv_full[ks], (item_n >> 1) & 1);  // key codes
-            const int4* mk4 = reinterpret_cast<const int4*>(smem + B_OFF_KV + ks * B_KV_STAGE + 2 * TILE_BYTES) + wg * 16;
-            const int jbase = kt * BT + wg * 64;
+            const int4* mk4 = reinterpret_cast<const int4*>(smem + B_OFF_KV + ks * B_KV_STAGE + 2 * TILE_BYTES) + wgi * 8;
+            const int jbase = kt * BT + wgi * 32;
             for (int n = 0; n < N; ++n, ++step_n) {
                 int hh, qt;
                 bwd_step(qmask, nph, n, hh, qt);
-                const int h = 2 * g + hh;
                 const int i = qt * BT + row;
-                float lse_i = INFINITY, dsum_i = 0.f;
-                int act_i = 0, sess_i = 0;
-                bool uni = false;
-                if (i < p.L) {
-                    const long long li = ((long long)b * p.n_q + h) * p.L + i;
-                    lse_i = p.lse[li];
-                    dsum_i = p.dsum[li];
-                    uni = (lse_i == INFINITY);
-                    if (kind_uses_act<KIND>()) act_i = p.act[(long long)b * p.L + i];
-                    if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
-                }
+                // per-row scalars travel with the Q / dO stage (padded copies: lse = +inf, dsum = 0 past L)
+                const int st = step_n & 1;
+                mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                const float* rowf = reinterpret_cast<const float*>(smem + B_OFF_QDO + st * B_QDO_STAGE + 2 * TILE_BYTES);
+                const float lse_i = rowf[row], dsum_i = rowf[128 + row];
+                const int act_i = reinterpret_cast<const int*>(rowf)[256 + row];
+                const int sess_i = reinterpret_cast<const int*>(rowf)[384 + row];
+                const bool uni = (i < p.L) && (lse_i == INFINITY);
                 const int istart = (i / p.P) * p.P;
                 const bool diag = kind_causal<KIND>() && (qt == kt);
                 const bool above = kind_causal<KIND>() && (qt < kt);  // only uniform rows reach keys above the diagonal
+                trace_pt(tr, 1, tn, 20);
                 mbar_wait(s_full, step_n & 1);
                 tc_fence_after();
-                uint32_t s[64];
+                trace_pt(tr, 1, tn, 21);
+                uint32_t s[32];
                 tmem_ld_32x32(t_s, s);
-                tmem_ld_32x32(t_s + 32, s + 32);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(s_free);
+                trace_pt(tr, 1, tn, 22);
                 // ---- P
-#pragma unroll
-                for (int c4 = 0; c4 < 16; ++c4) {
-                    int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
-                    if (KIND != MASK_SESSION) a4 = mk4[c4];
-                    if (kind_uses_sess<KIND>()) s4 = mk4[32 + c4];
-                    const int av[4] = {a4.x, a4.y, a4.z, a4.w};
-                    const int sv4[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = c4 * 4 + e;
-                        const int cc = wg * 64 + c;  // key column within the 128-key tile
-                        const int j = jbase + c;
-                        bool ok;
-                        if (above) ok = false;
-                        else if (diag) ok = allow_tc<KIND, true>(av[e], sv4[e], act_i, sess_i, cc, row, j, i, istart);
-                        else ok = allow_tc<KIND, false>(av[e], sv4[e], act_i, sess_i, cc, row, j, i, istart);
-                        float pv = ok ? ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse_i)) : 0.f;
-                        if (uni) pv = (j < p.L) ? p.inv_L : 0.f;
-                        s[c] = __float_as_uint(pv);
-                    }
+                {
+                    const int lim_u = uni ? (p.L - jbase) : 0;
+                    if (above)
+                        bwd_p_tile<KIND, 2>(s, mk4, act_i, sess_i, wgi * 32, row, jbase, i, istart, p.scale_log2, lse_i, lim_u, p.inv_L);
+                    else if (diag)
+                        bwd_p_tile<KIND, 1>(s, mk4, act_i, sess_i, wgi * 32, row, jbase, i, istart, p.scale_log2, lse_i, lim_u, p.inv_L);
+                    else
+                        bwd_p_tile<KIND, 0>(s, mk4, act_i, sess_i, wgi * 32, row, jbase, i, istart, p.scale_log2, lse_i, lim_u, p.inv_L);
                 }
+                trace_pt(tr, 1, tn, 23);
                 if (step_n > 0) mbar_wait(p_free, (step_n - 1) & 1);
+                trace_pt(tr, 1, tn, 24);
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    uint4 v;
-                    v.x = pack_bf16(__uint_as_float(s[8 * ch]), __uint_as_float(s[8 * ch + 1]));
-                    v.y = pack_bf16(__uint_as_float(s[8 * ch + 2]), __uint_as_float(s[8 * ch + 3]));
-                    v.z = pack_bf16(__uint_as_float(s[8 * ch + 4]), __uint_as_float(s[8 * ch + 5]));
-                    v.w = pack_bf16(__uint_as_float(s[8 * ch + 6]), __uint_as_float(s[8 * ch + 7]));
-                    *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t v0 = pack_bf16(__uint_as_float(s[8 * q]), __uint_as_float(s[8 * q + 1]));
+                    const uint32_t v1 = pack_bf16(__uint_as_float(s[8 * q + 2]), __uint_as_float(s[8 * q + 3]));
+                    const uint32_t v2 = pack_bf16(__uint_as_float(s[8 * q + 4]), __uint_as_float(s[8 * q + 5]));
+                    const uint32_t v3 = pack_bf16(__uint_as_float(s[8 * q + 6]), __uint_as_float(s[8 * q + 7]));
+                    sts128(sP + (((ch0 + q) ^ (row & 7)) << 4), v0, v1, v2, v3);
                 }
                 // ---- dS = P o (dP - dsum)
+                trace_pt(tr, 1, tn, 25);
                 mbar_wait(dp_full, step_n & 1);
                 tc_fence_after();
+                trace_pt(tr, 1, tn, 26);
                 if (step_n > 0) mbar_wait(ds_free, (step_n - 1) & 1);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                trace_pt(tr, 1, tn, 27);
+                {
                     uint32_t dp[32];
-                    tmem_ld_32x32(t_dp + half * 32, dp);
+                    tmem_ld_32x32(t_dp, dp);
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int c = half * 32 + q * 8 + 2 * e;
-                            const float d0 = __uint_as_float(s[c]) * (__uint_as_float(dp[q * 8 + 2 * e]) - dsum_i);
-                            const float d1 = __uint_as_float(s[c + 1]) * (__uint_as_float(dp[q * 8 + 2 * e + 1]) - dsum_i);
+                            const int c = q * 8 + 2 * e;
+                            const float d0 = __uint_as_float(s[c]) * (__uint_as_float(dp[c]) - dsum_i);
+                            const float d1 = __uint_as_float(s[c + 1]) * (__uint_as_float(dp[c + 1]) - dsum_i);
                             pk[e] = pack_bf16(d0, d1);
                         }
-                        const int ch = half * 4 + q;
-                        *reinterpret_cast<uint4*>(sDS + row * 128 + ((ch ^ (row & 7)) << 4)) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        sts128(sDS + (((ch0 + q) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
+                trace_pt(tr, 1, tn, 28);
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(pds_full);
+                trace_pt(tr, 1, tn, 29);
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 20) {
         // ===================== drain warps: dQ tiles -> TMA fp32 reduce-add; dK / dV -> bf16 TMA store ================
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
         const uint32_t t_dq = tmem_base + lane_off + T_DQ;
         uint8_t* stg = smem + B_OFF_STG;
+        const uint32_t stg_row = smem_u32(stg) + row * 128;
         uint32_t item_n = 0, step_n = 0;
+        int tn = 0;
+        Trace tr = p.tr;
+        if (row != 0) tr.buf = nullptr;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
             int b, g, kt;
             unsigned qmask;
@@ -742,26 +839,29 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int n = 0; n < N; ++n, ++step_n) {
                 int hh, qt;
                 bwd_step(qmask, nph, n, hh, qt);
+                trace_pt(tr, 2, tn, 40);
                 mbar_wait(dq_full, step_n & 1);
                 tc_fence_after();
-                uint32_t o[64];
-                tmem_ld_32x32(t_dq, o);
-                tmem_ld_32x32(t_dq + 32, o + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(dq_free);
+                trace_pt(tr, 2, tn, 41);
                 float* dst = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
-#pragma unroll
+#pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_dq + half * 32, o);
+                    tmem_ld_wait();
+                    if (half == 1) {
+                        tc_fence_before();
+                        mbar_arrive(dq_free);
+                    }
                     if (row == 0) bulk_wait_read0();  // the previous bulk op has finished reading the staging buffer
+                    trace_pt(tr, 2, tn, 42 + half);
                     named_bar_sync(3, 128);
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) {
-                        const int k = half * 32 + 4 * ch;
-                        const float4 v = make_float4(__uint_as_float(o[k]) * p.scale, __uint_as_float(o[k + 1]) * p.scale,
-                                                     __uint_as_float(o[k + 2]) * p.scale, __uint_as_float(o[k + 3]) * p.scale);
-                        *reinterpret_cast<float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
-                    }
+                    for (int ch = 0; ch < 8; ++ch)
+                        sts128(stg_row + ((ch ^ (row & 7)) << 4), __float_as_uint(__uint_as_float(o[4 * ch]) * p.scale),
+                               __float_as_uint(__uint_as_float(o[4 * ch + 1]) * p.scale),
+                               __float_as_uint(__uint_as_float(o[4 * ch + 2]) * p.scale),
+                               __float_as_uint(__uint_as_float(o[4 * ch + 3]) * p.scale));
                     fence_proxy_async();
                     named_bar_sync(3, 128);
                     if (row == 0) {
@@ -777,10 +877,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int which = 0; which < 2; ++which) {
                 const uint32_t t_acc = tmem_base + lane_off + (which == 0 ? T_DK : T_DV);
                 const float mul = (which == 0) ? p.scale : 1.f;
-                uint32_t o[64];
-                tmem_ld_32x32(t_acc, o);
-                tmem_ld_32x32(t_acc + 32, o + 32);
-                tmem_ld_wait();
+                uint32_t pk[32];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_acc + half * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        pk[half * 16 + k] = pack_bf16(__uint_as_float(o[2 * k]) * mul, __uint_as_float(o[2 * k + 1]) * mul);
+                }
                 if (which == 1) {
                     tc_fence_before();
                     mbar_arrive(dkv_free);
@@ -788,12 +894,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if (row == 0) bulk_wait_read0();
                 named_bar_sync(3, 128);
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * ch + e]) * mul;
-                    *reinterpret_cast<bf16x8*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = float_to_bf16x8(v);
-                }
+                for (int ch = 0; ch < 8; ++ch)
+                    sts128(stg_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
                 fence_proxy_async();
                 named_bar_sync(3, 128);
                 if (row == 0) {
@@ -809,12 +911,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// dsum[b,h,i] = sum_d dO*O ; uni_bits[b] |= 1 << (i / 128) for uniform rows (lse = +inf; head 0 decides: the mask is
-// head-independent)
+// Padded per-row inputs of the backward: dsum_p[b,h,i] = sum_d dO*O and lse_p[b,h,i] = lse (rows i >= L: 0 / +inf);
+// uni_bits[b] |= 1 << (i / 128) for uniform rows (lse = +inf; head 0 decides: the mask is head-independent)
 __global__ void attn_tc_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ld_o, int B,
-                                        int L, int n_q, const float* __restrict__ lse, float* __restrict__ dsum,
-                                        unsigned* __restrict__ uni_bits) {
-    const long long total = (long long)B * L * n_q;
+                                        int L, int Lp, int n_q, const float* __restrict__ lse, float* __restrict__ dsum_p,
+                                        float* __restrict__ lse_p, unsigned* __restrict__ uni_bits) {
+    const long long total = (long long)B * Lp * n_q;
     const int sub = threadIdx.x & 7;
     const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const long long gs = ((long long)gridDim.x * blockDim.x) >> 3;
@@ -822,22 +924,29 @@ __global__ void attn_tc_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* 
     for (long long it = 0; it < iters; ++it) {
         const long long gi = g0 + it * gs;
         const bool live = gi < total;
-        const long long row = live ? gi / n_q : 0;
+        const long long prow = live ? gi / n_q : 0;     // padded row index b * Lp + i
         const int h = live ? (int)(gi % n_q) : 0;
+        const int b = (int)(prow / Lp), i = (int)(prow % Lp);
+        const bool real = live && i < L;
+        const long long row = real ? (long long)b * L + i : 0;
         float a[8], d[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8), a);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8), d);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += a[i] * d[i];
+        for (int k = 0; k < 8; ++k) s += a[k] * d[k];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (live && sub == 0) {
-            const int b = (int)(row / L), i = (int)(row % L);
-            const long long li = ((long long)b * n_q + h) * L + i;
-            dsum[li] = s;
-            if (h == 0 && lse[li] == INFINITY) atomicOr(&uni_bits[b], 1u << (i / BT));
+            const long long pi = ((long long)b * n_q + h) * Lp + i;
+            float ls = INFINITY;
+            if (real) {
+                ls = lse[((long long)b * n_q + h) * L + i];
+                if (h == 0 && ls == INFINITY) atomicOr(&uni_bits[b], 1u << (i / BT));
+            }
+            dsum_p[pi] = real ? s : 0.f;
+            lse_p[pi] = ls;
         }
     }
 }
@@ -914,15 +1023,18 @@ inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
 struct MetaLayout {
     int Lp, k_tiles;
-    long long off_ka, off_ks, off_flag, bytes;
+    long long off_ka, off_ks, off_qa, off_qs, off_flag, bytes;
 };
 MetaLayout meta_layout(int B, int L) {
     MetaLayout m;
     m.k_tiles = (L + BT - 1) / BT;
     m.Lp = m.k_tiles * BT;
     m.off_ka = 0;
-    m.off_ks = align256((long long)B * m.Lp * 4);
-    m.off_flag = m.off_ks + align256((long long)B * m.Lp * 4);
+    const long long arr = align256((long long)B * m.Lp * 4);
+    m.off_ks = arr;
+    m.off_qa = 2 * arr;
+    m.off_qs = 3 * arr;
+    m.off_flag = 4 * arr;
     m.bytes = m.off_flag + align256((long long)B * m.k_tiles * 4);
     return m;
 }
@@ -934,6 +1046,8 @@ int build_meta(int kind, const int* am, const int* act, const int* sess, int B, 
     attn_meta_kernel<<<B * ml.k_tiles, BT, 0, stream>>>(am, act_in, sess_in, L, ml.Lp, ml.k_tiles,
                                                         reinterpret_cast<int*>(ws + ml.off_ka),
                                                         reinterpret_cast<int*>(ws + ml.off_ks),
+                                                        reinterpret_cast<int*>(ws + ml.off_qa),
+                                                        reinterpret_cast<int*>(ws + ml.off_qs),
                                                         reinterpret_cast<int*>(ws + ml.off_flag));
     GAMER_LAUNCH_CHECK();
     return 0;
@@ -969,6 +1083,13 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
 
 }  // namespace
 
+// debug hook: subsequent forward launches record a timeline of CTA 0 into buf (3 roles x cap x (tag, clock) int64 pairs)
+extern "C" int gamer_attn_set_trace(void* buf, int cap) {
+    g_trace.buf = reinterpret_cast<long long*>(buf);
+    g_trace.cap = cap;
+    return 0;
+}
+
 bool attn_tc_supported(int L, int n_q, int n_kv, int head_dim) {
     return head_dim == D && n_kv > 0 && n_q == 2 * n_kv && L >= 1 && (L + BT - 1) / BT <= 32;
 }
@@ -993,6 +1114,7 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
     p.ks = reinterpret_cast<const int*>(w8 + ml.off_ks);
     p.tflag = reinterpret_cast<const int*>(w8 + ml.off_flag);
     p.act = act; p.sess = sess; p.scale_log2 = scale * 1.4426950408889634f; p.vmean = vmean; p.lse = lse;
+    p.tr = g_trace;
     switch (kind) {
         case 0: return launch_fwd<0>(tq, tk, tv, to, p, stream);
         case 1: return launch_fwd<1>(tq, tk, tv, to, p, stream);
@@ -1003,13 +1125,14 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
 
 struct BwdLayout {
     MetaLayout ml;
-    long long off_dsum, off_uni, off_acc, acc_bytes, bytes;
+    long long off_dsum, off_lse, off_uni, off_acc, acc_bytes, bytes;
 };
 static BwdLayout bwd_layout(int B, int L, int n_q) {
     BwdLayout bl;
     bl.ml = meta_layout(B, L);
     bl.off_dsum = bl.ml.bytes;
-    bl.off_uni = bl.off_dsum + align256((long long)B * n_q * L * 4);
+    bl.off_lse = bl.off_dsum + align256((long long)B * n_q * bl.ml.Lp * 4);
+    bl.off_uni = bl.off_lse + align256((long long)B * n_q * bl.ml.Lp * 4);
     bl.off_acc = bl.off_uni + align256((long long)B * 4);
     bl.acc_bytes = (long long)B * n_q * bl.ml.k_tiles * DQ_TILE_FLOATS * 4;
     bl.bytes = bl.off_acc + align256(bl.acc_bytes);
@@ -1025,15 +1148,17 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     if (int e = build_meta(kind, am, act, sess, B, L, w8, bl.ml, stream)) return e;
     float* dsum = reinterpret_cast<float*>(w8 + bl.off_dsum);
+    float* lse_p = reinterpret_cast<float*>(w8 + bl.off_lse);
     unsigned* uni = reinterpret_cast<unsigned*>(w8 + bl.off_uni);
     float* acc = reinterpret_cast<float*>(w8 + bl.off_acc);
     // uni bits and the dQ accumulator are adjacent: one memset
     GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)(bl.off_acc - bl.off_uni) + (size_t)bl.acc_bytes, stream));
     {
-        const long long groups = (long long)B * L * n_q;
+        const long long groups = (long long)B * bl.ml.Lp * n_q;
         const long long blocks = (groups * 8 + 255) / 256;
         attn_tc_bwd_prep_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(
-            reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), ld_o, B, L, n_q, lse, dsum, uni);
+            reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), ld_o, B, L, bl.ml.Lp, n_q, lse, dsum, lse_p,
+            uni);
         GAMER_LAUNCH_CHECK();
     }
     CUtensorMap tq, tk, tv, tdo, tdk, tdv;
@@ -1048,8 +1173,11 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     p.q_tiles = bl.ml.k_tiles; p.k_tiles = bl.ml.k_tiles; p.total = B * n_kv * bl.ml.k_tiles;
     p.ka = reinterpret_cast<const int*>(w8 + bl.ml.off_ka);
     p.ks = reinterpret_cast<const int*>(w8 + bl.ml.off_ks);
-    p.act = act; p.sess = sess; p.lse = lse; p.dsum = dsum; p.uni_bits = uni;
+    p.qa = reinterpret_cast<const int*>(w8 + bl.ml.off_qa);
+    p.qs = reinterpret_cast<const int*>(w8 + bl.ml.off_qs);
+    p.lse_p = lse_p; p.dsum_p = dsum; p.uni_bits = uni;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.inv_L = 1.0f / (float)L; p.dq_acc = acc;
+    p.tr = g_trace;
     int e;
     switch (kind) {
         case 0: e = launch_bwd<0>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;

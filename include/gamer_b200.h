@@ -89,6 +89,8 @@ int gamer_ref_gemm_tn(const void* A, long long lda, const void* B, long long ldb
 
 /* ---- K6: masked attention (replaces mask materialisation + SDPA, Qwen3Multi/model.py:123-143,573-741) ---------- */
 long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv);
+/* debug hook (tools/attn_trace.py): record an in-kernel timeline of CTA 0 of the next forward launches; buf = NULL disables */
+int gamer_attn_set_trace(void* buf, int cap);
 int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
                    float scale, void* workspace, void* o, long long ld_o, float* lse, gamer_stream_t stream);
