@@ -32,35 +32,53 @@ struct GemmParams {
     float alpha;
 };
 
-template <int BLOCK_N>
-struct GemmSmem {
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+constexpr int BLOCK_N = 128;
+constexpr int TILE16K = 128 * 64 * 2;  // one [128 x 64] bf16 (or [128 x 32] fp32) SWIZZLE_128B box
+
+// STAGED: the epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (fully coalesced; the residual tile is
+// TMA-loaded into the same staging buffer beforehand and updated in place).  !STAGED: per-thread row stores, needed when
+// output rows are scattered through `row_map`.
+template <bool OUT_F32, bool STAGED>
+struct GemmCfg {
+    static constexpr int STAGES = STAGED ? (OUT_F32 ? 3 : 4) : 6;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int C_BUFS = STAGED ? (OUT_F32 ? 2 : 3) : 0;
+    static constexpr int C_BYTES = BLOCK_M * BLOCK_N * (OUT_F32 ? 4 : 2);
+    static constexpr int OFF_C = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_C + C_BUFS * C_BYTES;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024 /*align*/;
 };
 
-template <int BLOCK_N, bool OUT_F32>
+template <bool OUT_F32, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-    using S = GemmSmem<BLOCK_N>;
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
+    using S = GemmCfg<OUT_F32, STAGED>;
     constexpr int STAGES = S::STAGES;
-    constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512 (power of two)
+    constexpr int TMEM_COLS = 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* c_free = tempty_bar + 2;   // [3] staging buffer's TMA store has been read out
+    uint64_t* r_full = c_free + 3;       // [3] residual tile landed in the staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 3);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool has_resid = STAGED && p.resid != nullptr;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (STAGED) {
+            prefetch_tmap(&tmC);
+            if (has_resid) prefetch_tmap(&tmR);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -68,6 +86,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], 4);
+        }
+        for (int s = 0; s < 3; ++s) {
+            mbar_init(&c_free[s], 1);
+            mbar_init(&r_full[s], 1);
         }
         fence_barrier_init();
     }
@@ -105,8 +127,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            uint32_t phase = 0, tcount = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
                 const int m_blk = t / n_tiles, n_blk = t % n_tiles;
                 const int row0 = m_blk * BLOCK_M;
                 if (row0 >= row_end) break;
@@ -122,6 +144,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         stage = 0;
                         phase ^= 1;
                     }
+                }
+                if (has_resid) {
+                    const int cbuf = tcount % 3;
+                    const uint32_t use = tcount / 3;
+                    mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
+                    uint8_t* sc = smem + S::OFF_C + cbuf * S::C_BYTES;
+                    mbar_expect_tx(&r_full[cbuf], 2 * TILE16K);
+                    tma_load_2d(sc, &tmR, &r_full[cbuf], n_blk * BLOCK_N, row0);
+                    tma_load_2d(sc + TILE16K, &tmR, &r_full[cbuf], n_blk * BLOCK_N + 64, row0);
                 }
             }
         }
@@ -167,73 +198,138 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int trow = quarter * 32 + lane;
         int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        uint32_t acc_phase = 0, tcount = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
             const int m_blk = t / n_tiles, n_blk = t % n_tiles;
             const int row0 = m_blk * BLOCK_M;
             if (row0 >= row_end) break;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const int row = row0 + quarter * 32 + lane;
-            long long orow = -1;
-            if (row < row_end) orow = (p.row_map != nullptr) ? (long long)p.row_map[row] : (long long)row;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c, r);
-                tmem_ld_wait();
-                const int col0 = n_blk * BLOCK_N + c;
-                if (orow >= 0 && col0 < p.N) {
-                    float v[32];
+            if constexpr (STAGED) {
+                const int cbuf = tcount % S::C_BUFS;
+                const uint32_t use = tcount / S::C_BUFS;
+                if (has_resid) mbar_wait(&r_full[cbuf], use & 1);
+                else mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t sc = smem_u32(smem + S::OFF_C + cbuf * S::C_BYTES) + trow * 128;
+                const uint32_t sw = trow & 7;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-                    const bool full = (col0 + 32 <= p.N);
-                    if (p.resid != nullptr) {
-                        const bf16* rp = p.resid + orow * p.ldr + col0;
-                        if (full) {
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if constexpr (OUT_F32) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                bf16x8 rv = *reinterpret_cast<const bf16x8*>(rp + 8 * q);
+                        for (int q = 0; q < 8; ++q)
+                            sts128(sc + c * TILE16K + ((q ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * q]) * p.alpha),
+                                   __float_as_uint(__uint_as_float(r[4 * q + 1]) * p.alpha),
+                                   __float_as_uint(__uint_as_float(r[4 * q + 2]) * p.alpha),
+                                   __float_as_uint(__uint_as_float(r[4 * q + 3]) * p.alpha));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t addr = sc + (c >> 1) * TILE16K + ((((c & 1) * 4 + q) ^ sw) << 4);
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]) * p.alpha;
+                            if (has_resid) {
+                                bf16x8 rv;
+                                lds128(addr, rv.u[0], rv.u[1], rv.u[2], rv.u[3]);
                                 float f[8];
                                 bf16x8_to_float(rv, f);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[8 * q + i] += f[i];
+                                for (int i = 0; i < 8; ++i) v[i] += f[i];
                             }
-                        } else {
-                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += __bfloat162float(rp[i]);
-                        }
-                    }
-                    if constexpr (OUT_F32) {
-                        float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + col0;
-                        if (full) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<float4*>(cp + 4 * q) =
-                                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        } else {
-                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = v[i];
-                        }
-                    } else {
-                        bf16* cp = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + col0;
-                        if (full) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) *reinterpret_cast<bf16x8*>(cp + 8 * q) = float_to_bf16x8(v + 8 * q);
-                        } else {
-                            for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = __float2bfloat16(v[i]);
+                            const bf16x8 o = float_to_bf16x8(v);
+                            sts128(addr, o.u[0], o.u[1], o.u[2], o.u[3]);
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (warp == 2 && lane == 0) {
+                    constexpr int NBOX = OUT_F32 ? 4 : 2;
+                    constexpr int BOX_COLS = OUT_F32 ? 32 : 64;
+                    const uint8_t* sbuf = smem + S::OFF_C + cbuf * S::C_BYTES;
+#pragma unroll
+                    for (int bx = 0; bx < NBOX; ++bx)
+                        if (n_blk * BLOCK_N + bx * BOX_COLS < p.N)
+                            tma_store_2d(&tmC, sbuf + bx * TILE16K, n_blk * BLOCK_N + bx * BOX_COLS, row0);
+                    bulk_commit();
+                    if (tcount > 0) {  // every store but the one just issued has been read out: recycle its buffer
+                        bulk_wait_read1();
+                        mbar_arrive(&c_free[(tcount - 1) % S::C_BUFS]);
+                    }
+                }
+            } else {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const int row = row0 + trow;
+                long long orow = -1;
+                if (row < row_end) orow = (p.row_map != nullptr) ? (long long)p.row_map[row] : (long long)row;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c, r);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BLOCK_N + c;
+                    if (orow >= 0 && col0 < p.N) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                        const bool full = (col0 + 32 <= p.N);
+                        if (p.resid != nullptr) {
+                            const bf16* rp = p.resid + orow * p.ldr + col0;
+                            if (full) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    bf16x8 rv = *reinterpret_cast<const bf16x8*>(rp + 8 * q);
+                                    float f[8];
+                                    bf16x8_to_float(rv, f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[8 * q + i] += f[i];
+                                }
+                            } else {
+                                for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += __bfloat162float(rp[i]);
+                            }
+                        }
+                        if constexpr (OUT_F32) {
+                            float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + col0;
+                            if (full) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    *reinterpret_cast<float4*>(cp + 4 * q) =
+                                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {
+                                for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = v[i];
+                            }
+                        } else {
+                            bf16* cp = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + col0;
+                            if (full) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<bf16x8*>(cp + 8 * q) = float_to_bf16x8(v + 8 * q);
+                            } else {
+                                for (int i = 0; i < 32 && col0 + i < p.N; ++i) cp[i] = __float2bfloat16(v[i]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (STAGED && warp == 2 && lane == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -489,10 +585,29 @@ int num_sms() {
     return n;
 }
 
-template <int BLOCK_N, bool OUT_F32>
-int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    using S = GemmSmem<BLOCK_N>;
-    auto kern = gemm_tn_kernel<BLOCK_N, OUT_F32>;
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [128 rows, 32 cols] (128 bytes), SWIZZLE_128B.
+int make_tmap_f32(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    GAMER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    GAMER_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0,
+                  "fp32 TMA output must be 16-byte aligned (ld=%lld)", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
+                  cols, ld);
+    return 0;
+}
+
+template <bool OUT_F32, bool STAGED>
+int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                   const GemmParams& p, cudaStream_t stream) {
+    using S = GemmCfg<OUT_F32, STAGED>;
+    auto kern = gemm_tn_kernel<OUT_F32, STAGED>;
     static bool configured = false;
     if (!configured) {
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -500,7 +615,7 @@ int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPar
     }
     const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+    kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
@@ -518,14 +633,28 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
                   "C rows must be 16-byte aligned (ldc=%lld)", ldc);
     GAMER_REQUIRE(resid == nullptr || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0),
                   "residual rows must be 16-byte aligned (ldr=%lld)", ldr);
-    CUtensorMap tmA, tmB;
-    const int block_n = (N % 256 == 0) ? 256 : 128;
+    CUtensorMap tmA, tmB, tmC, tmR;
     if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;
-    if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, block_n)) return e;
+    if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, BLOCK_N)) return e;
     GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha};
-    if (block_n == 256)
-        return c_is_f32 ? launch_gemm_tn<256, true>(tmA, tmB, p, stream) : launch_gemm_tn<256, false>(tmA, tmB, p, stream);
-    return c_is_f32 ? launch_gemm_tn<128, true>(tmA, tmB, p, stream) : launch_gemm_tn<128, false>(tmA, tmB, p, stream);
+    // staged (TMA-store) epilogue whenever output rows are the A rows; fp32 outputs carry no residual in this code base
+    const bool staged = row_map == nullptr && !(c_is_f32 && resid != nullptr);
+    if (!staged) {
+        tmC = tmA;
+        tmR = tmA;
+        return c_is_f32 ? launch_gemm_tn<true, false>(tmA, tmB, tmC, tmR, p, stream)
+                        : launch_gemm_tn<false, false>(tmA, tmB, tmC, tmR, p, stream);
+    }
+    if (c_is_f32) {
+        if (int e = make_tmap_f32(&tmC, C, rows, N, ldc)) return e;
+        tmR = tmA;
+        return launch_gemm_tn<true, true>(tmA, tmB, tmC, tmR, p, stream);
+    }
+    if (int e = make_tmap_bf16(&tmC, C, rows, N, ldc, BLOCK_M)) return e;
+    tmR = tmA;
+    if (resid != nullptr)
+        if (int e = make_tmap_bf16(&tmR, resid, rows, N, ldr, BLOCK_M)) return e;
+    return launch_gemm_tn<false, true>(tmA, tmB, tmC, tmR, p, stream);
 }
 
 extern "C" int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* X, long long ldx, int rows, int N_out,

@@ -52,11 +52,13 @@ def allowed_by_last_token(tree: PrefixTree, last_token_set: set[int], sentence: 
 
 def constrained_beam_search(spec: om.Spec, W: dict, tree: PrefixTree, last_token_set: set[int], input_ids,
                             attention_mask, session_ids=None, extended_session_ids=None, actions=None,
-                            num_beams: int = 20, max_new_tokens: int = 4):
+                            num_beams: int = 20, max_new_tokens: int = 4, trace: list | None = None):
     """Returns (sequences [B*K, L+new] int64, sequences_scores [B*K] fp32), best-first per user — the same
     contract as `generate(..., num_beams=K, num_return_sequences=K, output_scores=True)`.
 
     Every user's prompt is expanded to K identical rows (as HF does) so cache handling is a plain row gather.
+    `trace` (test aid), when a list, receives per step (kept sequences [B,K,L+s+1], kept running scores [B,K],
+    running score of the best pruned candidate [B]) so a test can tell how close a hypothesis came to the pruning cut.
     """
     B, L = input_ids.shape
     K, V = num_beams, spec.vocab_size
@@ -77,12 +79,15 @@ def constrained_beam_search(spec: om.Spec, W: dict, tree: PrefixTree, last_token
             mask[r, allowed] = 0
         acc = (logp + mask).view(B, K, V) + running[:, :, None]
         top_val, top_idx = torch.topk(acc.view(B, K * V), k=2 * K)             # HF keeps max(2,1+n_eos)*K
+        first_pruned = top_val[:, K].clone()
         top_val, top_idx = top_val[:, :K], top_idx[:, :K]                      # nothing can finish early: top-K
         beam = top_idx // V
         tok = top_idx % V
         seqs = torch.cat([torch.gather(seqs, 1, beam[:, :, None].expand(-1, -1, seqs.shape[2])),
                           tok[:, :, None]], dim=2)
         running = top_val
+        if trace is not None:
+            trace.append((seqs.clone(), running.clone(), first_pruned))
         if step + 1 < max_new_tokens:
             rows = (beam + torch.arange(B)[:, None] * K).view(-1)
             st.reorder(rows)
