@@ -342,13 +342,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // rows), UMMA descriptors with LBO = 8192 (next 64-wide MN atom = next box) and SBO = 1024 (next 8 k-rows).
 // Work item = (group, row chunk, i-block, j-block); partial sums are reduced with fp32 red.global.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int W_CHUNK_ROWS = 2048;
 constexpr int W_STAGES = 4;
 constexpr int W_BOX_BYTES = 64 * 64 * 2;           // 8 KB
 constexpr int W_A_BYTES = 2 * W_BOX_BYTES;         // 128 output rows (i)
 constexpr int W_B_BYTES = 4 * W_BOX_BYTES;         // up to 256 output cols (j)
 constexpr int W_STAGE_BYTES = W_A_BYTES + W_B_BYTES;
-constexpr int W_SMEM_TOTAL = W_STAGES * W_STAGE_BYTES + 1024 + 256;
+constexpr int W_OFF_STG = W_STAGES * W_STAGE_BYTES;  // 2 x [128 rows x 32 fp32] staging boxes for the reduce-add epilogue
+constexpr int W_OFF_BAR = W_OFF_STG + 2 * TILE16K;
+constexpr int W_SMEM_TOTAL = W_OFF_BAR + 256 + 1024;
 
 struct WgradParams {
     int rows, N_out, K_in, n_groups;
@@ -356,13 +357,15 @@ struct WgradParams {
     float* dW;
     int bj;        // j-block width (multiple of 64, <= 256)
     int n_i, n_j;  // output tile grid
+    int chunk_rows;  // token rows per work item (multiple of 64): sized on the host so one wave of CTAs covers the work
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+             const __grid_constant__ CUtensorMap tmW, WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + W_STAGES * W_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + W_OFF_BAR);
     uint64_t* empty_bar = full_bar + W_STAGES;
     uint64_t* tfull_bar = empty_bar + W_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -405,7 +408,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
         gbeg[g] = b;
         gend[g] = e;
-        cstart[g + 1] = cstart[g] + (max(e - b, 0) + W_CHUNK_ROWS - 1) / W_CHUNK_ROWS;
+        cstart[g + 1] = cstart[g] + (max(e - b, 0) + p.chunk_rows - 1) / p.chunk_rows;
     }
     const int n_ij = p.n_i * p.n_j;
     const int total = cstart[MAX_GROUPS] * n_ij;
@@ -424,8 +427,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < MAX_GROUPS; ++i)
             if (i == g) {
-                r0 = gbeg[i] + (chunk - cstart[i]) * W_CHUNK_ROWS;
-                r1 = min(r0 + W_CHUNK_ROWS, gend[i]);
+                r0 = gbeg[i] + (chunk - cstart[i]) * p.chunk_rows;
+                r1 = min(r0 + p.chunk_rows, gend[i]);
             }
     };
 
@@ -490,24 +493,32 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     } else {
         const int quarter = warp & 3;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, box_n = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             int g, r0, r1, ib, jb;
             decode(w, g, r0, r1, ib, jb);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int i = ib * 128 + quarter * 32 + lane;
+            // TMEM -> registers -> swizzled [128 x 32] fp32 staging box -> TMA reduce-add into dW (rows / columns past the
+            // matrix edge are clipped by the tensor map).  Two staging boxes alternate.
+            const int trow = quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
-            float* out = p.dW + ((long long)g * p.N_out + i) * p.K_in;
-            for (int c = 0; c < p.bj; c += 32) {
+            for (int c = 0; c < p.bj; c += 32, ++box_n) {
                 uint32_t rr[32];
                 tmem_ld_32x32(taddr + c, rr);
                 tmem_ld_wait();
-                const int j0 = jb * p.bj + c;
-                if (i < p.N_out) {
+                uint8_t* stg = smem + W_OFF_STG + (box_n & 1) * TILE16K;
+                if (warp == 2 && lane == 0 && box_n >= 2) bulk_wait_read1();  // the box issued two steps ago has been read
+                named_bar_sync(1, 128);
+                const uint32_t srow = smem_u32(stg) + trow * 128;
 #pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        if (j0 + q < p.K_in) atomicAdd(out + j0 + q, __uint_as_float(rr[q]));
+                for (int q = 0; q < 8; ++q)
+                    sts128(srow + ((q ^ (trow & 7)) << 4), rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (warp == 2 && lane == 0) {
+                    if (jb * p.bj + c < p.K_in) tma_reduce_add_3d(&tmW, stg, jb * p.bj + c, ib * 128, g);
+                    bulk_commit();
                 }
             }
             tc_fence_before();
@@ -519,6 +530,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             }
         }
     }
+    if (warp == 2 && lane == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -675,15 +687,36 @@ extern "C" int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* 
     p.n_i = ceil_div(N_out, 128);
     p.n_j = ceil_div(K_in, 256);
     p.bj = ceil_div(ceil_div(K_in, p.n_j), 64) * 64;
+    // dW as [n_groups][N_out][K_in] fp32: box = [1][128 rows][32 cols]
+    CUtensorMap tmW;
+    {
+        EncodeTiledFn fn = get_encode_fn();
+        GAMER_REQUIRE((reinterpret_cast<uintptr_t>(dW) & 15) == 0 && (K_in * 4) % 16 == 0,
+                      "wgrad output rows must be 16-byte aligned (K_in=%d)", K_in);
+        cuuint64_t dims[3] = {(cuuint64_t)K_in, (cuuint64_t)N_out, (cuuint64_t)n_groups};
+        cuuint64_t strides[2] = {(cuuint64_t)K_in * 4, (cuuint64_t)N_out * K_in * 4};
+        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = fn(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (dW) failed with %d (N_out=%d K_in=%d groups=%d)", (int)r, N_out,
+                      K_in, n_groups);
+    }
     static bool configured = false;
     if (!configured) {
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_TOTAL));
         configured = true;
     }
+    // chunk the token rows so that (groups x tiles x chunks) fills one wave of CTAs as evenly as possible
+    const int tiles = n_groups * p.n_i * p.n_j;
+    const int chunks_per_group = tiles >= num_sms() ? 1 : num_sms() / tiles;
+    const int rows_per_group = ceil_div(rows, n_groups);
+    p.chunk_rows = ceil_div(ceil_div(rows_per_group, chunks_per_group), 64) * 64;
+    if (p.chunk_rows < 256) p.chunk_rows = 256;
     // upper bound on work items (grouped: every group may add one partial chunk)
-    const long long items = (long long)(ceil_div(rows, W_CHUNK_ROWS) + n_groups) * p.n_i * p.n_j;
+    const long long items = (long long)(ceil_div(rows, p.chunk_rows) + n_groups) * p.n_i * p.n_j;
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    wgrad_kernel<<<grid, NUM_THREADS, W_SMEM_TOTAL, stream>>>(tmY, tmX, p);
+    wgrad_kernel<<<grid, NUM_THREADS, W_SMEM_TOTAL, stream>>>(tmY, tmX, tmW, p);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
