@@ -48,7 +48,9 @@ __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const float* __re
 //   dx[m] = (dres ? dres[m] : 0) + rstd*g - x*rstd^3*mean(g.x),  g = w*dh
 //   dw   += sum_m dh*x*rstd        (block partials -> fp32 atomics)
 //   dcat[cat_idx[m]] += dh[m, H:H+cat_dim]
-__global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+template <bool HAS_CAT>
+__global__ void __launch_bounds__(256, HAS_CAT ? 3 : 4)
+rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ rstd_in, float eps, long long M,
                                    const bf16* __restrict__ dh, long long ld_dh, const int* __restrict__ row_map,
                                    const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dw,
@@ -61,12 +63,13 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    float wv[8], dwacc[8], catacc[4][8];
+    float wv[8], dwacc[8], catacc[HAS_CAT ? 4 : 1][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         wv[i] = w[lane * 8 + i];
         dwacc[i] = 0.f;
-        catacc[0][i] = catacc[1][i] = catacc[2][i] = catacc[3][i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (HAS_CAT ? 4 : 1); ++q) catacc[q][i] = 0.f;
     }
     for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
         float xf[8], df[8];
@@ -101,7 +104,7 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
             for (int i = 0; i < 8; ++i) o[i] += rf[i];
         }
         *reinterpret_cast<bf16x8*>(dx + m * H256 + lane * 8) = float_to_bf16x8(o);
-        if (dcat != nullptr && lane < cat_dim / 8) {
+        if (HAS_CAT && lane < cat_dim / 8) {
             float cf[8];
             bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + H256 + lane * 8), cf);
             const int r = cat_idx[m];
@@ -118,9 +121,9 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
             }
         }
     }
-    if (dcat != nullptr && lane < cat_dim / 8) {
+    if (HAS_CAT && lane < cat_dim / 8) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < (HAS_CAT ? 4 : 1); ++q)
             if (q < cat_rows) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) atomicAdd(&scat[q * cat_dim + lane * 8 + i], catacc[q][i]);
@@ -130,7 +133,7 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __re
     for (int i = 0; i < 8; ++i) atomicAdd(&sdw[lane * 8 + i], dwacc[i]);
     __syncthreads();
     for (int i = threadIdx.x; i < H256; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
-    if (dcat != nullptr)
+    if (HAS_CAT)
         for (int i = threadIdx.x; i < cat_rows * cat_dim; i += blockDim.x)
             if (scat[i] != 0.f) atomicAdd(&dcat[i], scat[i]);
 }
@@ -160,67 +163,95 @@ struct HeadArgs {
     float eps;
 };
 
-__global__ void qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw,
-                                        bf16* __restrict__ out, long long ld_out) {
-    const int n_heads = a.n_q + 2 * a.n_kv;
-    const int sub = threadIdx.x & 7;           // lane within the head group
-    const long long groups = a.M * n_heads;
-    const long long gid0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long gstride = ((long long)gridDim.x * blockDim.x) >> 3;
-    // uniform trip count: the 4 head groups of a warp may be q, k or v heads, so every shuffle below is executed by
-    // all 32 lanes and results are selected afterwards
-    const long long iters = (groups + gstride - 1) / gstride;
+// Thread block = (8 lanes, n_heads, Z tokens): a thread keeps one head for the whole kernel and walks tokens with stride
+// gridDim.x * Z.  Lane j of a head holds columns [4j, 4j+4) of the first half and [32+4j, 32+4j+4) of the second half, so
+// the RoPE partner of every element is in the same thread (no shuffles) and cos/sin are one float4 each.
+struct HeadRow {
+    float f[8];  // [0,4): first-half columns, [4,8): second-half columns
+};
+__device__ __forceinline__ HeadRow load_head_row(const bf16* p, int sub) {
+    const uint2 lo = *reinterpret_cast<const uint2*>(p + 4 * sub);
+    const uint2 hi = *reinterpret_cast<const uint2*>(p + 32 + 4 * sub);
+    HeadRow r;
+    float2 t;
+    t = unpack_bf16(lo.x); r.f[0] = t.x; r.f[1] = t.y;
+    t = unpack_bf16(lo.y); r.f[2] = t.x; r.f[3] = t.y;
+    t = unpack_bf16(hi.x); r.f[4] = t.x; r.f[5] = t.y;
+    t = unpack_bf16(hi.y); r.f[6] = t.x; r.f[7] = t.y;
+    return r;
+}
+__device__ __forceinline__ void store_head_row(bf16* p, int sub, const float* f) {
+    *reinterpret_cast<uint2*>(p + 4 * sub) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+    *reinterpret_cast<uint2*>(p + 32 + 4 * sub) = make_uint2(pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+template <bool HAS_EMB>
+__global__ void __launch_bounds__(384)
+qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw, bf16* __restrict__ out,
+                        long long ld_out) {
+    const int sub = threadIdx.x, h = threadIdx.y, Z = blockDim.z;
+    const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
+    const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
+    const int width = is_q ? a.n_q * HD : a.n_kv * HD;
+    const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD;
+    const float* wn = is_q ? a.qn_w : a.kn_w;
+    const float4 w_lo = *reinterpret_cast<const float4*>(wn + 4 * sub);
+    const float4 w_hi = *reinterpret_cast<const float4*>(wn + 32 + 4 * sub);
+    const float wv[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
+    const long long m_stride = (long long)gridDim.x * Z;
+    const long long m0 = (long long)blockIdx.x * Z + threadIdx.z;
+    const long long iters = (a.M + m_stride - 1) / m_stride;   // uniform trip count: shuffles run in full warps
+    int pos = (int)(m0 % a.L);
+    const int pstep = (int)(m_stride % a.L);
     for (long long it = 0; it < iters; ++it) {
-        const long long gidx = gid0 + it * gstride;
-        const bool live = gidx < groups;
-        const long long m = live ? gidx / n_heads : 0;
-        const int h = live ? (int)(gidx % n_heads) : 0;
-        const int col = h * HD + sub * 8;
-        float f[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(raw + m * ld_raw + col), f);
-        const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
-        const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
-        if (emb != nullptr) {
-            const int width = is_q ? a.n_q * HD : a.n_kv * HD;
-            const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
-            float e[8];
-            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(emb + (long long)a.act_idx[m] * width + hc), e);
+        const long long mm = m0 + it * m_stride;
+        const bool live = mm < a.M;
+        const long long m = live ? mm : 0;
+        HeadRow u = load_head_row(raw + m * ld_raw + h * HD, sub);
+        if (HAS_EMB) {
+            const HeadRow e = load_head_row(emb + (long long)a.act_idx[m] * width + hc, sub);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += e[i];
+            for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
+        const int p = a.pos_ids ? a.pos_ids[m] : (live ? pos : 0) + a.pos0;
+        const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
+        const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
+        const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
         float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-        const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
-        const float* wn = is_q ? a.qn_w : a.kn_w;
-        const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
-        const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
-        const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
+        for (int i = 0; i < 8; ++i) ss += u.f[i] * u.f[i];
+        const float rstd = rsqrtf(group8_sum(ss) * (1.0f / HD) + a.eps);
         float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float n = wn[sub * 8 + i] * (f[i] * rstd);
-            const float partner = __shfl_xor_sync(0xffffffffu, n, 4);
-            o[i] = n * ct[i] + ((sub < 4) ? -partner : partner) * st[i];
-        }
         if (is_q || is_k) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = o[i];
+            for (int i = 0; i < 4; ++i) {
+                const float n1 = wv[i] * (u.f[i] * rstd), n2 = wv[4 + i] * (u.f[4 + i] * rstd);
+                o[i] = n1 * cs[i] - n2 * sn[i];
+                o[4 + i] = n2 * cs[i] + n1 * sn[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = u.f[i];
         }
-        if (live) *reinterpret_cast<bf16x8*>(out + m * ld_out + col) = float_to_bf16x8(f);
+        if (live) store_head_row(out + m * ld_out + h * HD, sub, o);
+        pos += pstep;
+        if (pos >= a.L) pos -= a.L;
     }
 }
 
 // backward: d_out (grad wrt rotated q,k and v) -> d_raw; accumulates d qn_w / d kn_w and the behaviour-embedding grads.
-// Every 8-lane group keeps ONE head for the whole kernel (group g -> head g % n_heads, tokens strided), so the
-// norm-weight and behaviour-embedding partial sums live in registers ([emb_rows <= 4][8 columns] per lane) and are
-// flushed once per thread: no per-token atomics.
+// A thread keeps ONE head for the whole kernel, so the norm-weight and behaviour-embedding partial sums live in
+// registers ([emb_rows <= 4][8 columns] per lane) and are flushed once per thread: no per-token atomics.
 constexpr int MAX_EMB_ROWS = 4;
 
-__global__ void __launch_bounds__(256)
+template <bool HAS_EMB>
+__global__ void __launch_bounds__(384, 2)
 qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw, const bf16* __restrict__ dout,
                         long long ld_dout, bf16* __restrict__ draw, long long ld_draw, float* __restrict__ d_qn_w,
                         float* __restrict__ d_kn_w, float* __restrict__ d_q_emb, float* __restrict__ d_k_emb,
@@ -230,83 +261,80 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
     const int emb_w = n_heads * HD;
     float* sdw = sh;
     float* semb = sh + 2 * HD;
-    const bool has_emb = d_q_emb != nullptr;
-    for (int i = threadIdx.x; i < 2 * HD + (has_emb ? emb_rows * emb_w : 0); i += blockDim.x) sh[i] = 0.f;
+    const int tid = threadIdx.x + 8 * (threadIdx.y + n_heads * threadIdx.z);
+    const int nthr = 8 * n_heads * blockDim.z;
+    for (int i = tid; i < 2 * HD + (HAS_EMB ? emb_rows * emb_w : 0); i += nthr) sh[i] = 0.f;
     __syncthreads();
-    const int sub = threadIdx.x & 7;
-    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;      // launch guarantees n_groups % n_heads == 0
-    const int h = (int)(group % n_heads);
-    const long long m0 = group / n_heads, m_stride = n_groups / n_heads;
-    const long long iters = (a.M + m_stride - 1) / m_stride;
-    const int col = h * HD + sub * 8;
+    const int sub = threadIdx.x, h = threadIdx.y, Z = blockDim.z;
     const bool is_q = h < a.n_q, is_k = !is_q && h < a.n_q + a.n_kv;
     const bf16* emb = is_q ? a.q_emb : (is_k ? a.k_emb : a.v_emb);
     const int width = is_q ? a.n_q * HD : a.n_kv * HD;
-    const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD + sub * 8;
+    const int hc = (is_q ? h : (is_k ? h - a.n_q : h - a.n_q - a.n_kv)) * HD;
     const float* wn = is_q ? a.qn_w : a.kn_w;
-    float wv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wv[i] = wn[sub * 8 + i];
+    const float4 w_lo = *reinterpret_cast<const float4*>(wn + 4 * sub);
+    const float4 w_hi = *reinterpret_cast<const float4*>(wn + 32 + 4 * sub);
+    const float wv[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
     float dwn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float demb[MAX_EMB_ROWS][8];
+    float demb[HAS_EMB ? MAX_EMB_ROWS : 1][8];
 #pragma unroll
-    for (int r = 0; r < MAX_EMB_ROWS; ++r)
+    for (int r = 0; r < (HAS_EMB ? MAX_EMB_ROWS : 1); ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) demb[r][i] = 0.f;
 
+    const long long m_stride = (long long)gridDim.x * Z;
+    const long long m0 = (long long)blockIdx.x * Z + threadIdx.z;
+    const long long iters = (a.M + m_stride - 1) / m_stride;
+    int pos = (int)(m0 % a.L);
+    const int pstep = (int)(m_stride % a.L);
     for (long long it = 0; it < iters; ++it) {
         const long long mm = m0 + it * m_stride;
         const bool live = mm < a.M;
         const long long m = live ? mm : 0;
-        float u[8], d[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(raw + m * ld_raw + col), u);
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + m * ld_dout + col), d);
-        const int act = (has_emb && live) ? a.act_idx[m] : 0;
-        if (has_emb) {
-            float e[8];
-            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(emb + (long long)act * width + hc), e);
+        HeadRow u = load_head_row(raw + m * ld_raw + h * HD, sub);
+        const HeadRow d = load_head_row(dout + m * ld_dout + h * HD, sub);
+        int act = 0;
+        if (HAS_EMB) {
+            act = live ? a.act_idx[m] : 0;
+            const HeadRow e = load_head_row(emb + (long long)act * width + hc, sub);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] += e[i];
+            for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
+        const int p = a.pos_ids ? a.pos_ids[m] : (live ? pos : 0) + a.pos0;
+        const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
+        const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
+        const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+        // every lane runs the group reductions (a warp mixes q/k and v heads); v heads discard the result
         float du[8];
-        const int pos = a.pos_ids ? a.pos_ids[m] : (int)(m % a.L) + a.pos0;
-        const float* ct = a.cos_tab + (long long)pos * 32 + (sub & 3) * 8;
-        const float* st = a.sin_tab + (long long)pos * 32 + (sub & 3) * 8;
         float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += u[i] * u[i];
-        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-        const float rstd = rsqrtf(ss * (1.0f / HD) + a.eps);
+        for (int i = 0; i < 8; ++i) ss += u.f[i] * u.f[i];
+        const float rstd = rsqrtf(group8_sum(ss) * (1.0f / HD) + a.eps);
         float dn[8], dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float partner = __shfl_xor_sync(0xffffffffu, d[i], 4);
-            // transpose of the rotation: first half gets +sin * d[second], second half gets -sin * d[first]
-            dn[i] = d[i] * ct[i] + ((sub < 4) ? partner : -partner) * st[i];
-            const float g = wv[i] * dn[i];
-            dot += g * u[i];
-            du[i] = g;
+        for (int i = 0; i < 4; ++i) {
+            // transpose of the rotation
+            dn[i] = d.f[i] * cs[i] + d.f[4 + i] * sn[i];
+            dn[4 + i] = d.f[4 + i] * cs[i] - d.f[i] * sn[i];
         }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        dot *= (1.0f / HD) * rstd * rstd * rstd;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            du[i] = wv[i] * dn[i];
+            dot += du[i] * u.f[i];
+        }
+        dot = group8_sum(dot) * (1.0f / HD) * rstd * rstd * rstd;
         if (is_q || is_k) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                dwn[i] += live ? dn[i] * u[i] * rstd : 0.f;
-                du[i] = rstd * du[i] - u[i] * dot;
+                dwn[i] += live ? dn[i] * u.f[i] * rstd : 0.f;
+                du[i] = rstd * du[i] - u.f[i] * dot;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) du[i] = d[i];
+            for (int i = 0; i < 8; ++i) du[i] = d.f[i];
         }
         if (live) {
-            *reinterpret_cast<bf16x8*>(draw + m * ld_draw + col) = float_to_bf16x8(du);
-            if (has_emb) {
+            store_head_row(draw + m * ld_draw + h * HD, sub, du);
+            if (HAS_EMB) {
 #pragma unroll
                 for (int r = 0; r < MAX_EMB_ROWS; ++r)
                     if (r == act) {
@@ -315,27 +343,31 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
                     }
             }
         }
+        pos += pstep;
+        if (pos >= a.L) pos -= a.L;
     }
+    // this thread's columns within the head: 4*sub + i (i < 4), 32 + 4*sub + (i - 4)
     if (is_q || is_k) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&sdw[(is_q ? 0 : HD) + sub * 8 + i], dwn[i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(&sdw[(is_q ? 0 : HD) + (i < 4 ? 4 * sub + i : 28 + 4 * sub + i)], dwn[i]);
     }
-    if (has_emb) {
+    if (HAS_EMB) {
 #pragma unroll
         for (int r = 0; r < MAX_EMB_ROWS; ++r)
             if (r < emb_rows) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(&semb[r * emb_w + col + i], demb[r][i]);
+                for (int i = 0; i < 8; ++i)
+                    atomicAdd(&semb[r * emb_w + h * HD + (i < 4 ? 4 * sub + i : 28 + 4 * sub + i)], demb[r][i]);
             }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < HD; i += blockDim.x) {
+    for (int i = tid; i < HD; i += nthr) {
         if (sdw[i] != 0.f) atomicAdd(&d_qn_w[i], sdw[i]);
         if (sdw[HD + i] != 0.f) atomicAdd(&d_kn_w[i], sdw[HD + i]);
     }
-    if (has_emb) {
+    if (HAS_EMB) {
         const int qw = a.n_q * HD, kw = a.n_kv * HD;
-        for (int i = threadIdx.x; i < emb_rows * emb_w; i += blockDim.x) {
+        for (int i = tid; i < emb_rows * emb_w; i += nthr) {
             const float v = semb[i];
             if (v == 0.f) continue;
             const int r = i / emb_w, c = i % emb_w;
@@ -370,12 +402,17 @@ extern "C" int gamer_rmsnorm_bwd(const void* x, const float* w, const float* rst
     GAMER_REQUIRE(H == H256, "rmsnorm kernels are specialised for hidden size 256 (got %d)", H);
     if (M == 0) return 0;
     const int wpb = 8;
-    const int grid = (int)((M + wpb - 1) / wpb < 148 * 4 ? (M + wpb - 1) / wpb : 148 * 4);
+    const int grid = (int)((M + wpb - 1) / wpb < 148 * 8 ? (M + wpb - 1) / wpb : 148 * 8);
     const int cr = dcat ? cat_rows : 0;
     const size_t smem = (H256 + cr * cat_dim) * sizeof(float);
-    rmsnorm_bwd_kernel<<<grid, wpb * 32, smem, stream>>>(
-        reinterpret_cast<const bf16*>(x), w, rstd, eps, M, reinterpret_cast<const bf16*>(dh), ld_dh, row_map,
-        reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dw, cat_idx, cat_dim, cr, dcat);
+    if (dcat != nullptr)
+        rmsnorm_bwd_kernel<true><<<grid, wpb * 32, smem, stream>>>(
+            reinterpret_cast<const bf16*>(x), w, rstd, eps, M, reinterpret_cast<const bf16*>(dh), ld_dh, row_map,
+            reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dw, cat_idx, cat_dim, cr, dcat);
+    else
+        rmsnorm_bwd_kernel<false><<<grid, wpb * 32, smem, stream>>>(
+            reinterpret_cast<const bf16*>(x), w, rstd, eps, M, reinterpret_cast<const bf16*>(dh), ld_dh, row_map,
+            reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dw, cat_idx, cat_dim, cr, dcat);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
@@ -400,11 +437,18 @@ extern "C" int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* o
     if (M == 0) return 0;
     HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
                                 act_idx, eps);
-    const long long groups = M * (n_q + 2 * n_kv);
-    const long long blocks = (groups * 8 + 255) / 256;
-    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    qk_norm_rope_fwd_kernel<<<grid, 256, 0, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
-                                                      reinterpret_cast<bf16*>(out), ld_out);
+    const int n_heads = n_q + 2 * n_kv;
+    GAMER_REQUIRE(n_heads <= 48, "too many heads for the (8, heads, Z) block layout");
+    const int Z = n_heads <= 12 ? 4 : (n_heads <= 24 ? 2 : 1);
+    const dim3 block(8, n_heads, Z);
+    const long long want = (M + Z - 1) / Z;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    if (q_emb != nullptr)
+        qk_norm_rope_fwd_kernel<true><<<grid, block, 0, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
+                                                                  reinterpret_cast<bf16*>(out), ld_out);
+    else
+        qk_norm_rope_fwd_kernel<false><<<grid, block, 0, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
+                                                                   reinterpret_cast<bf16*>(out), ld_out);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
@@ -425,16 +469,20 @@ extern "C" int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const v
     const size_t smem = (2 * HD + (has_emb ? emb_rows * (n_q + 2 * n_kv) * HD : 0)) * sizeof(float);
     GAMER_REQUIRE(smem <= 48 * 1024, "too many behaviour rows for the shared-memory accumulator");
     GAMER_REQUIRE(!has_emb || emb_rows <= MAX_EMB_ROWS, "at most %d behaviour-embedding rows (num_behavior + 1)", MAX_EMB_ROWS);
-    // 32 groups per block; the number of groups must be a multiple of n_heads so each group keeps one head
     const int n_heads = n_q + 2 * n_kv;
-    int grid = 148 * 4;
-    const long long want = (M * n_heads + 31) / 32;
-    if (want < grid) grid = (int)want;
-    grid = (grid + n_heads - 1) / n_heads * n_heads;      // 32 * grid divisible by n_heads when grid is
-    qk_norm_rope_bwd_kernel<<<grid, 256, smem, stream>>>(a, reinterpret_cast<const bf16*>(raw), ld_raw,
-                                                         reinterpret_cast<const bf16*>(dout), ld_dout,
-                                                         reinterpret_cast<bf16*>(draw), ld_draw, d_qn_w, d_kn_w,
-                                                         has_emb ? d_q_emb : nullptr, d_k_emb, d_v_emb, emb_rows);
+    GAMER_REQUIRE(n_heads <= 48, "too many heads for the (8, heads, Z) block layout");
+    const int Z = n_heads <= 12 ? 4 : (n_heads <= 24 ? 2 : 1);
+    const dim3 block(8, n_heads, Z);
+    const long long want = (M + Z - 1) / Z;
+    const int grid = (int)(want < 148 * 3 ? want : 148 * 3);
+    if (has_emb)
+        qk_norm_rope_bwd_kernel<true><<<grid, block, smem, stream>>>(
+            a, reinterpret_cast<const bf16*>(raw), ld_raw, reinterpret_cast<const bf16*>(dout), ld_dout,
+            reinterpret_cast<bf16*>(draw), ld_draw, d_qn_w, d_kn_w, d_q_emb, d_k_emb, d_v_emb, emb_rows);
+    else
+        qk_norm_rope_bwd_kernel<false><<<grid, block, smem, stream>>>(
+            a, reinterpret_cast<const bf16*>(raw), ld_raw, reinterpret_cast<const bf16*>(dout), ld_dout,
+            reinterpret_cast<bf16*>(draw), ld_draw, d_qn_w, d_kn_w, nullptr, nullptr, nullptr, emb_rows);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
