@@ -15,6 +15,8 @@
 // evaluated per (query, key) from per-key codes that fold the key padding mask in (attn_meta_kernel).  Rows with no
 // allowed key are "uniform rows" (quirk Q1): forward output = column mean of V over all L keys, lse = +inf; backward uses
 // P = 1/L over all keys (the analytic gradient of that uniform softmax).
+#include <stdlib.h>
+
 #include "attention_tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -476,6 +478,283 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+
+// =================================================================================================================
+// forward, "small CTA" variant: one 128-thread CTA per (sequence, query head, 128-query tile), 64-key tiles, three CTAs
+// resident per SM (TMEM: 128 columns each, smem ~66 KB each).  Inside a CTA everything is sequential — thread 0 issues
+// the TMA loads and the MMAs, all four warps run the softmax (one query row per thread, the whole 64-key row of the
+// tile in registers, so the row max needs no exchange) — and the latencies of one CTA are hidden by the other two.
+// The exp2 throughput (16 / clk / SM) is what bounds it.
+// =================================================================================================================
+constexpr int S_KT = 64;                                   // keys per tile
+constexpr int S_HALF = S_KT * D * 2;                       // 8 KB: one [64 x 64] bf16 tile
+constexpr int S_OFF_Q = 0;                                 // [128 x 64] Q, later the O staging tile
+constexpr int S_OFF_K = TILE_BYTES;                        // 2 stages
+constexpr int S_OFF_V = S_OFF_K + 2 * S_HALF;              // 2 stages
+constexpr int S_OFF_P = S_OFF_V + 2 * S_HALF;              // [128 q x 64 keys] bf16
+constexpr int S_OFF_C = S_OFF_P + TILE_BYTES;              // key codes ring: 4 x (ka[64] | ks[64])
+constexpr int S_OFF_BAR = S_OFF_C + 4 * 512;
+constexpr int S_SMEM = S_OFF_BAR + 128 + 1024;
+constexpr int S_THREADS = 160;                             // 4 softmax warps + 1 issuer warp
+
+template <int KIND, bool DIAG, bool CODES>
+__device__ __forceinline__ float mask_max64(uint32_t (&s)[64], const int4* mk4, int act_i, int sess_i, int cc0, int row, int j0,
+                                            int i, int istart) {
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+        int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
+        if (CODES && KIND != MASK_SESSION) a4 = mk4[c4];
+        if (CODES && kind_uses_sess<KIND>()) s4 = mk4[16 + c4];
+        const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            const bool ok = allow_tc<KIND, DIAG>(av[e], sv[e], act_i, sess_i, cc0 + c, row, j0 + c, i, istart);
+            const float v = ok ? __uint_as_float(s[c]) : -INFINITY;
+            s[c] = __float_as_uint(v);
+            mx[e] = fmaxf(mx[e], v);
+        }
+    }
+    return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+}
+
+// cold path: multiply this thread's O row (64 fp32 TMEM columns) by alpha
+__device__ __noinline__ void rescale_o_row64(uint32_t t_o, float alpha) {
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + hh * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+        tmem_st_32x32(t_o + hh * 32, o);
+    }
+    tmem_st_wait();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(S_THREADS, 3)
+attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;   // [2]
+    uint64_t* v_full = bars + 3;   // [2]
+    uint64_t* c_full = bars + 5;   // [4] key codes
+    uint64_t* s_full = bars + 9;
+    uint64_t* s_free = bars + 10;  // all softmax threads have read S out of TMEM
+    uint64_t* p_full = bars + 11;  // P tile written (and O rescaled)
+    uint64_t* o_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    // work item: heaviest query tiles first
+    const int per = p.B * p.n_q;
+    const int qt = p.q_tiles - 1 - (int)blockIdx.x / per;
+    const int rem = (int)blockIdx.x % per;
+    const int b = rem / p.n_q, h = rem % p.n_q;
+    const int g = h / (p.n_q / p.n_kv);
+    const int kt_all = (p.L + S_KT - 1) / S_KT;
+    const int nkt = kind_causal<KIND>() ? min(2 * (qt + 1), kt_all) : kt_all;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmQ);
+        prefetch_tmap(&tmK);
+        prefetch_tmap(&tmV);
+        prefetch_tmap(&tmO);
+        for (int i = 0; i < 13; ++i) mbar_init(&bars[i], (i == 10 || i == 11) ? 128 : 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<128>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sq = smem_u32(smem + S_OFF_Q), sp = smem_u32(smem + S_OFF_P);
+
+    if (warp == 4) {
+        // ===================== issuer: TMA loads + MMAs =====================
+        if ((threadIdx.x & 31) == 0) {
+            auto load_k = [&](int j) {  // K tile j and its key codes
+                const int st = j & 1, cs = j & 3;
+                mbar_expect_tx(&k_full[st], S_HALF);
+                tma_load_3d(smem + S_OFF_K + st * S_HALF, &tmK, &k_full[st], g * D, j * S_KT, b);
+                mbar_expect_tx(&c_full[cs], 512);
+                bulk_load_1d(smem + S_OFF_C + cs * 512, p.ka + (long long)b * p.Lp + j * S_KT, 256, &c_full[cs]);
+                bulk_load_1d(smem + S_OFF_C + cs * 512 + 256, p.ks + (long long)b * p.Lp + j * S_KT, 256, &c_full[cs]);
+            };
+            auto load_v = [&](int j) {
+                const int st = j & 1;
+                mbar_expect_tx(&v_full[st], S_HALF);
+                tma_load_3d(smem + S_OFF_V + st * S_HALF, &tmV, &v_full[st], g * D, j * S_KT, b);
+            };
+            auto issue_s = [&](int j) {  // S[128 x 64] = Q K_j^T
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+                const uint32_t sk = smem_u32(smem + S_OFF_K + (j & 1) * S_HALF);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, desc_k(sq + k * 32), desc_k(sk + k * 32), idesc, k != 0);
+                umma_commit(s_full);
+            };
+            auto issue_pv = [&](int j) {  // O[128 x 64] (+)= P[128 x 64 keys] V_j[64 keys x 64]
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+                const uint32_t sv = smem_u32(smem + S_OFF_V + (j & 1) * S_HALF);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + 64, desc_k(sp + k * 32), desc_mn(sv + k * 2048, S_HALF), idesc,
+                              (j > 0 || k != 0) ? 1u : 0u);
+                umma_commit(o_full);
+            };
+            mbar_expect_tx(q_full, TILE_BYTES);
+            tma_load_3d(smem + S_OFF_Q, &tmQ, q_full, h * D, qt * BT, b);
+            load_k(0);
+            load_v(0);
+            if (nkt > 1) {
+                load_k(1);
+                load_v(1);
+            }
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nkt; ++j) {
+                if (j + 1 < nkt) {  // S(j+1) as soon as S(j) has been read out of TMEM
+                    mbar_wait(s_free, j & 1);
+                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    tc_fence_after();
+                    issue_s(j + 1);
+                    // K_j is dead (S(j) completed before it was read out): prefetch two tiles ahead.  The codes slot
+                    // (j+2)&3 was last read during tile j-2, which p_full(j-2) (waited below, last iteration) closes.
+                    if (j + 2 < nkt) load_k(j + 2);
+                }
+                mbar_wait(p_full, j & 1);
+                mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+                // wait for PV(j-1) BEFORE issuing PV(j): a parity wait must never fall two phases behind its barrier
+                if (j >= 1) mbar_wait(o_full, (j - 1) & 1);
+                tc_fence_after();
+                issue_pv(j);
+                if (j >= 1 && j + 1 < nkt) load_v(j + 1);  // the V stage of tile j-1 is free
+            }
+        }
+    } else {
+        // ===================== softmax: one query row per thread =====================
+        const int row = threadIdx.x;
+        const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t t_o = t_s + 64;
+        const int i = qt * BT + row;
+        int act_i = 0, sess_i = 0;
+        if (i < p.L) {
+            if (kind_uses_act<KIND>()) act_i = p.act[(long long)b * p.L + i];
+            if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
+        }
+        const int istart = (i / p.P) * p.P;
+        unsigned allvalid = 0;  // bit t: every key of 128-key tile t is valid (CAUSAL tiles off the diagonal need no mask)
+        if (KIND == MASK_CAUSAL) {
+            for (int t = 0; t < p.k_tiles; ++t) allvalid |= (p.tflag[b * p.k_tiles + t] != 0 ? 1u : 0u) << t;
+        }
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < nkt; ++j) {
+            mbar_wait(&c_full[j & 3], (j >> 2) & 1);
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t s[64];
+            tmem_ld_32x32(t_s, s);
+            tmem_ld_32x32(t_s + 32, s + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            const int4* mk4 = reinterpret_cast<const int4*>(smem + S_OFF_C + (j & 3) * 512);
+            // keys of this tile relative to the query tile's first row (only the diagonal band needs the j <= i test)
+            const int cc0 = j * S_KT - qt * BT;
+            const bool diag = kind_causal<KIND>() && (cc0 + S_KT - 1 > 0);
+            const bool codes = (KIND != MASK_CAUSAL) || (((allvalid >> (j >> 1)) & 1u) == 0);
+            float mx;
+            if (codes) {
+                if (diag) mx = mask_max64<KIND, true, true>(s, mk4, act_i, sess_i, cc0, row, j * S_KT, i, istart);
+                else mx = mask_max64<KIND, false, true>(s, mk4, act_i, sess_i, cc0, row, j * S_KT, i, istart);
+            } else if (diag) {
+                mx = mask_max64<KIND, true, false>(s, mk4, act_i, sess_i, cc0, row, j * S_KT, i, istart);
+            } else {
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(s[c]));
+                mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            }
+            // lazy running max (log2 domain): raise it only from -inf or by more than 2^64
+            const float m_tile = mx * p.scale_log2;
+            float m_new = m;
+            if (m == -INFINITY) m_new = m_tile;
+            else if (m_tile > m + 64.f) m_new = m_tile;
+            const bool rescale = (m != -INFINITY) && (m_new != m);
+            if (rescale) l *= ex2_approx(m - m_new);
+            const float m_old = m;
+            m = m_new;
+            const float neg_m = (m == -INFINITY) ? 0.f : -m;
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
+                sum[(c >> 1) & 1] += p0;
+                sum[2 + ((c >> 1) & 1)] += p1;
+                s[c >> 1] = pack_bf16(p0, p1);
+            }
+            l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+            if (j > 0) {
+                mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) done: O stable, P buffer free
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, rescale)) rescale_o_row64(t_o, rescale ? ex2_approx(m_old - m_new) : 1.f);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                sts128(sp + row * 128 + ((ch ^ (row & 7)) << 4), s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l (or the V column mean on uniform rows) -> bf16 -> smem (the dead Q tile) -> TMA store
+        mbar_wait(o_full, (nkt - 1) & 1);
+        tc_fence_after();
+        const bool uniform = !(l > 0.f);
+        const float inv = uniform ? 0.f : 1.f / l;
+        const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * q + e]) * inv;
+                if (uniform) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = vm[hh * 32 + 8 * q + e];
+                }
+                const int ch = hh * 4 + q;
+                const bf16x8 ov = float_to_bf16x8(v);
+                sts128(sq + row * 128 + ((ch ^ (row & 7)) << 4), ov.u[0], ov.u[1], ov.u[2], ov.u[3]);
+            }
+        }
+        if (i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m + log2f(l));
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+            tma_store_3d(&tmO, smem + S_OFF_Q, h * D, qt * BT, b);
+            bulk_commit();
+            bulk_wait0();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<128>(tmem_base);
 }
 
 // =================================================================================================================
@@ -992,14 +1271,14 @@ EncodeTiledFn encode_fn() {
 }
 
 // bf16 [B][L][cols] view (row stride ld elements, sequence stride L*ld); box = [1][128 rows][64 cols], SWIZZLE_128B
-int make_tmap_seq(CUtensorMap* m, const void* base, int B, int L, int cols, long long ld) {
+int make_tmap_seq(CUtensorMap* m, const void* base, int B, int L, int cols, long long ld, int box_rows = 128) {
     EncodeTiledFn fn = encode_fn();
     GAMER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
     GAMER_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
                   "attention operands must be 16-byte aligned (ld=%lld)", ld);
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1068,6 +1347,19 @@ int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
 }
 
 template <int KIND>
+int launch_fwd_small(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                     const FwdParams& p, cudaStream_t stream) {
+    static bool cfg = false;
+    if (!cfg) {
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_small_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+        cfg = true;
+    }
+    attn_fwd_small_kernel<KIND><<<p.B * p.n_q * p.q_tiles, S_THREADS, S_SMEM, stream>>>(tq, tk, tv, to, p);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
     static bool cfg = false;
@@ -1102,10 +1394,16 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
     const MetaLayout ml = meta_layout(B, L);
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     if (int e = build_meta(kind, am, act, sess, B, L, w8, ml, stream)) return e;
+    static int use_ws = -1;  // GAMER_ATTN_FWD_WS=1: the warp-specialised GQA ping-pong kernel instead of the small-CTA one
+    if (use_ws < 0) {
+        const char* e = getenv("GAMER_ATTN_FWD_WS");
+        use_ws = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    const int kv_box = use_ws ? 128 : S_KT;
     CUtensorMap tq, tk, tv, to;
     if (int e = make_tmap_seq(&tq, q, B, L, n_q * D, ld)) return e;
-    if (int e = make_tmap_seq(&tk, k, B, L, n_kv * D, ld)) return e;
-    if (int e = make_tmap_seq(&tv, v, B, L, n_kv * D, ld)) return e;
+    if (int e = make_tmap_seq(&tk, k, B, L, n_kv * D, ld, kv_box)) return e;
+    if (int e = make_tmap_seq(&tv, v, B, L, n_kv * D, ld, kv_box)) return e;
     if (int e = make_tmap_seq(&to, o, B, L, n_q * D, ld_o)) return e;
     FwdParams p{};
     p.B = B; p.L = L; p.Lp = ml.Lp; p.n_q = n_q; p.n_kv = n_kv; p.P = P;
@@ -1115,6 +1413,14 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
     p.tflag = reinterpret_cast<const int*>(w8 + ml.off_flag);
     p.act = act; p.sess = sess; p.scale_log2 = scale * 1.4426950408889634f; p.vmean = vmean; p.lse = lse;
     p.tr = g_trace;
+    if (!use_ws) {
+        switch (kind) {
+            case 0: return launch_fwd_small<0>(tq, tk, tv, to, p, stream);
+            case 1: return launch_fwd_small<1>(tq, tk, tv, to, p, stream);
+            case 2: return launch_fwd_small<2>(tq, tk, tv, to, p, stream);
+            default: return launch_fwd_small<3>(tq, tk, tv, to, p, stream);
+        }
+    }
     switch (kind) {
         case 0: return launch_fwd<0>(tq, tk, tv, to, p, stream);
         case 1: return launch_fwd<1>(tq, tk, tv, to, p, stream);
