@@ -8,7 +8,7 @@ mkdir -p $OUT
 BENCH="python bench.py --steps 1 --warmup 1 --global-batch 128 --micro-batch 128 --no-cpu-baseline"
 # every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.stdout 2>&1
-for K in attn_bwd_dkv_kernel attn_bwd_dq_kernel attn_fwd_kernel gemm_tn_kernel wgrad_kernel embed_route_kernel emb_reduce_kernel; do
+for K in ${KERNELS:-attn_tc_bwd_kernel attn_fwd_small_kernel gemm_tn_kernel wgrad_kernel embed_route_kernel emb_reduce_kernel}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 2 -f -o $OUT/prof_${TAG}_$K $BENCH > $OUT/prof_${TAG}_$K.stdout 2>&1
 done
 ls -la $OUT | tail -20
