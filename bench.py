@@ -280,7 +280,8 @@ def main():
                 "config": {"workload": f"Qwen3Multi smb_explicit_decoder train (configs[1]), max_his_len={args.max_his_len}, "
                                        f"L={L}, global batch {args.global_batch}, full-length rows, fwd+bwd+allreduce+clip+AdamW",
                            "global_batch": args.global_batch, "per_gpu_batch": B_local, "micro_batch": mb, "seq_len": L,
-                           "parallelism": f"dp{world}", "tokens_per_s": value * L, "dropout": "off (round 1: not yet in kernels)",
+                           "parallelism": f"dp{world}", "tokens_per_s": value * L, "dropout": f"on (train mode: dropout_rate={cfg.dropout_rate}, attention_dropout={cfg.attention_dropout}, "
+                                      f"Philox masks regenerated in the backward)",
                            "l2_policy": "inputs and activations (>1 GB per micro-batch) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,

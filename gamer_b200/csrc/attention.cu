@@ -667,7 +667,7 @@ extern "C" long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv)
 extern "C" int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                               int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act,
                               const int* sess, float scale, void* workspace, void* o, long long ld_o, float* lse,
-                              cudaStream_t stream) {
+                              const gamer_dropout_t* drop, cudaStream_t stream) {
     if (int e = check_common(n_q, n_kv, head_dim, mask_kind, act, sess)) return e;
     if (B == 0 || L == 0) return 0;
     AttnArgs a{};
@@ -680,7 +680,8 @@ extern "C" int gamer_attn_fwd(const void* q, const void* k, const void* v, long 
     GAMER_LAUNCH_CHECK();
     if (use_tc(L, n_q, n_kv, head_dim))
         return attn_tc_fwd(q, k, v, ld, B, L, n_q, n_kv, mask_kind, tokens_per_item, am, act, sess, scale, a.vmean,
-                           reinterpret_cast<uint8_t*>(workspace) + vmean_bytes(B, n_kv), o, ld_o, lse, stream);
+                           reinterpret_cast<uint8_t*>(workspace) + vmean_bytes(B, n_kv), o, ld_o, lse, drop, stream);
+    GAMER_REQUIRE(drop == nullptr || !(drop->p > 0.f), "attention dropout needs the tcgen05 path (head_dim 64, GQA 2:1, L <= 4096)");
     dim3 grid((L + BQ - 1) / BQ, n_q, B);
     static bool cfg = false;
     if (!cfg) {
@@ -709,12 +710,13 @@ extern "C" int gamer_attn_bwd(const void* q, const void* k, const void* v, long 
                               int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act,
                               const int* sess, float scale, const void* o, const void* d_o, long long ld_o,
                               const float* lse, void* workspace, void* dq, void* dk, void* dv, long long ld_d,
-                              cudaStream_t stream) {
+                              const gamer_dropout_t* drop, cudaStream_t stream) {
     if (int e = check_common(n_q, n_kv, head_dim, mask_kind, act, sess)) return e;
     if (B == 0 || L == 0) return 0;
     if (use_tc(L, n_q, n_kv, head_dim))
         return attn_tc_bwd(q, k, v, ld, B, L, n_q, n_kv, mask_kind, tokens_per_item, am, act, sess, scale, o, d_o, ld_o, lse,
-                           workspace, dq, dk, dv, ld_d, stream);
+                           workspace, dq, dk, dv, ld_d, drop, stream);
+    GAMER_REQUIRE(drop == nullptr || !(drop->p > 0.f), "attention dropout needs the tcgen05 path (head_dim 64, GQA 2:1, L <= 4096)");
     const int q_tiles = (L + BQ - 1) / BQ;
     float* dsum = reinterpret_cast<float*>(workspace);
     int* uni = reinterpret_cast<int*>(dsum + (long long)B * n_q * L);

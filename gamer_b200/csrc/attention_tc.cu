@@ -157,6 +157,7 @@ struct FwdParams {
     float scale_log2;
     const float* vmean;
     float* lse;
+    DropParams drop;  // attention-probability dropout (8-bit thresholds); thresh == 0: off
     Trace tr;
 };
 
@@ -536,7 +537,11 @@ __device__ __noinline__ void rescale_o_row64(uint32_t t_o, float alpha) {
     tmem_st_wait();
 }
 
-template <int KIND>
+// Dropout of the probabilities (SDPA dropout_p, Qwen3Multi/model.py:139): P is zeroed where the Philox byte of (sequence,
+// head, query, key) is below the threshold; the row sum l keeps the undropped P (softmax normalisation happens before
+// dropout) and the 1/keep scale is folded into the final O / l.  Uniform rows (quirk Q1) take their expectation: the
+// column mean of V, no dropout.
+template <int KIND, bool DROP>
 __global__ void __launch_bounds__(S_THREADS, 3)
 attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, FwdParams p) {
@@ -696,13 +701,33 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             m = m_new;
             const float neg_m = (m == -INFINITY) ? 0.f : -m;
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (DROP) {
 #pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
-                sum[(c >> 1) & 1] += p0;
-                sum[2 + ((c >> 1) & 1)] += p1;
-                s[c >> 1] = pack_bf16(p0, p1);
+                for (int cb = 0; cb < 4; ++cb) {
+                    const uint4 rnd = drop_attn16(p.drop, (uint32_t)(b * p.n_q + h), (uint32_t)i, (uint32_t)(j * 4 + cb));
+                    const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const int c = cb * 16 + e;
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
+                        sum[(c >> 1) & 1] += p0;
+                        sum[2 + ((c >> 1) & 1)] += p1;
+                        const uint32_t w = rw[e >> 2];
+                        const bool k0 = ((w >> (8 * (e & 3))) & 0xffu) >= p.drop.thresh;
+                        const bool k1 = ((w >> (8 * (e & 3) + 8)) & 0xffu) >= p.drop.thresh;
+                        s[c >> 1] = pack_bf16(k0 ? p0 : 0.f, k1 ? p1 : 0.f);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 64; c += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
+                    sum[(c >> 1) & 1] += p0;
+                    sum[2 + ((c >> 1) & 1)] += p1;
+                    s[c >> 1] = pack_bf16(p0, p1);
+                }
             }
             l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
             if (j > 0) {
@@ -721,7 +746,7 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(o_full, (nkt - 1) & 1);
         tc_fence_after();
         const bool uniform = !(l > 0.f);
-        const float inv = uniform ? 0.f : 1.f / l;
+        const float inv = uniform ? 0.f : (DROP ? p.drop.scale : 1.f) / l;
         const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -783,6 +808,7 @@ struct BwdParams {
     const unsigned* uni_bits;  // [B]: bit qt = query tile qt holds a uniform row
     float scale, scale_log2, inv_L;
     float* dq_acc;       // [B, n_q, q_tiles][2 halves][128 rows][32 floats], 16-byte chunks XOR-swizzled by (row & 7)
+    DropParams drop;     // the forward's attention-probability dropout, regenerated here
     Trace tr;
 };
 
@@ -836,7 +862,9 @@ __device__ __forceinline__ void bwd_p_tile(uint32_t (&s)[32], const int4* mk4, i
     }
 }
 
-template <int KIND>
+// With dropout (DROP): O = (P o Z) V, Z = keep / keep_prob.  dV += (P o Z)^T dO; dS = P o (Z o dP - dsum) with
+// dsum = rowsum(dO o O) unchanged.  Uniform rows carry no dropout (Z = 1), as in the forward.
+template <int KIND, bool DROP>
 __global__ void __launch_bounds__(B_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -1057,15 +1085,40 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         bwd_p_tile<KIND, 0>(s, mk4, act_i, sess_i, wgi * 32, row, jbase, i, istart, p.scale_log2, lse_i, lim_u, p.inv_L);
                 }
                 trace_pt(tr, 1, tn, 23);
+                // keep bits of this thread's 32 (query, key) pairs; zs = 1 / keep probability (1 on uniform rows)
+                uint32_t keep = 0xffffffffu;
+                float zs = 1.f;
+                if constexpr (DROP) {
+                    if (!uni) {
+                        keep = 0u;
+                        zs = p.drop.scale;
+#pragma unroll
+                        for (int cb = 0; cb < 2; ++cb) {
+                            const uint4 rnd = drop_attn16(p.drop, (uint32_t)(b * p.n_q + 2 * g + hh), (uint32_t)i,
+                                                          (uint32_t)((jbase >> 4) + cb));
+                            const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                keep |= ((((rw[e >> 2] >> (8 * (e & 3))) & 0xffu) >= p.drop.thresh) ? 1u : 0u) << (cb * 16 + e);
+                        }
+                    }
+                }
                 if (step_n > 0) mbar_wait(p_free, (step_n - 1) & 1);
                 trace_pt(tr, 1, tn, 24);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint32_t v0 = pack_bf16(__uint_as_float(s[8 * q]), __uint_as_float(s[8 * q + 1]));
-                    const uint32_t v1 = pack_bf16(__uint_as_float(s[8 * q + 2]), __uint_as_float(s[8 * q + 3]));
-                    const uint32_t v2 = pack_bf16(__uint_as_float(s[8 * q + 4]), __uint_as_float(s[8 * q + 5]));
-                    const uint32_t v3 = pack_bf16(__uint_as_float(s[8 * q + 6]), __uint_as_float(s[8 * q + 7]));
-                    sts128(sP + (((ch0 + q) ^ (row & 7)) << 4), v0, v1, v2, v3);
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = q * 8 + 2 * e;
+                        float p0 = __uint_as_float(s[c]), p1 = __uint_as_float(s[c + 1]);
+                        if constexpr (DROP) {
+                            p0 = ((keep >> c) & 1u) ? p0 * zs : 0.f;
+                            p1 = ((keep >> (c + 1)) & 1u) ? p1 * zs : 0.f;
+                        }
+                        pk[e] = pack_bf16(p0, p1);
+                    }
+                    sts128(sP + (((ch0 + q) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
                 // ---- dS = P o (dP - dsum)
                 trace_pt(tr, 1, tn, 25);
@@ -1084,8 +1137,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int c = q * 8 + 2 * e;
-                            const float d0 = __uint_as_float(s[c]) * (__uint_as_float(dp[c]) - dsum_i);
-                            const float d1 = __uint_as_float(s[c + 1]) * (__uint_as_float(dp[c + 1]) - dsum_i);
+                            float g0 = __uint_as_float(dp[c]), g1 = __uint_as_float(dp[c + 1]);
+                            if constexpr (DROP) {
+                                g0 = ((keep >> c) & 1u) ? g0 * zs : 0.f;
+                                g1 = ((keep >> (c + 1)) & 1u) ? g1 * zs : 0.f;
+                            }
+                            const float d0 = __uint_as_float(s[c]) * (g0 - dsum_i);
+                            const float d1 = __uint_as_float(s[c + 1]) * (g1 - dsum_i);
                             pk[e] = pack_bf16(d0, d1);
                         }
                         sts128(sDS + (((ch0 + q) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
@@ -1346,31 +1404,43 @@ int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
     return 0;
 }
 
-template <int KIND>
-int launch_fwd_small(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                     const FwdParams& p, cudaStream_t stream) {
+template <int KIND, bool DROP>
+int launch_fwd_small_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                       const FwdParams& p, cudaStream_t stream) {
     static bool cfg = false;
     if (!cfg) {
-        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_small_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_small_kernel<KIND, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
         cfg = true;
     }
-    attn_fwd_small_kernel<KIND><<<p.B * p.n_q * p.q_tiles, S_THREADS, S_SMEM, stream>>>(tq, tk, tv, to, p);
+    attn_fwd_small_kernel<KIND, DROP><<<p.B * p.n_q * p.q_tiles, S_THREADS, S_SMEM, stream>>>(tq, tk, tv, to, p);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
-
 template <int KIND>
-int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-               const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
+int launch_fwd_small(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                     const FwdParams& p, cudaStream_t stream) {
+    return p.drop.thresh ? launch_fwd_small_t<KIND, true>(tq, tk, tv, to, p, stream)
+                         : launch_fwd_small_t<KIND, false>(tq, tk, tv, to, p, stream);
+}
+
+template <int KIND, bool DROP>
+int launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                 const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
     static bool cfg = false;
     if (!cfg) {
-        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KIND, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
         cfg = true;
     }
     const int grid = p.total < sm_count() ? p.total : sm_count();
-    attn_tc_bwd_kernel<KIND><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+    attn_tc_bwd_kernel<KIND, DROP><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
     GAMER_LAUNCH_CHECK();
     return 0;
+}
+template <int KIND>
+int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+               const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
+    return p.drop.thresh ? launch_bwd_t<KIND, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
+                         : launch_bwd_t<KIND, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
 }
 
 }  // namespace
@@ -1390,7 +1460,7 @@ long long attn_tc_fwd_ws_bytes(int B, int L) { return meta_layout(B, L).bytes; }
 
 int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv, int kind, int P,
                 const int* am, const int* act, const int* sess, float scale, const float* vmean, void* ws, void* o,
-                long long ld_o, float* lse, cudaStream_t stream) {
+                long long ld_o, float* lse, const gamer_dropout_t* drop, cudaStream_t stream) {
     const MetaLayout ml = meta_layout(B, L);
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     if (int e = build_meta(kind, am, act, sess, B, L, w8, ml, stream)) return e;
@@ -1413,6 +1483,8 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
     p.tflag = reinterpret_cast<const int*>(w8 + ml.off_flag);
     p.act = act; p.sess = sess; p.scale_log2 = scale * 1.4426950408889634f; p.vmean = vmean; p.lse = lse;
     p.tr = g_trace;
+    p.drop = make_drop(drop, 8);
+    GAMER_REQUIRE(!(use_ws && p.drop.thresh), "attention dropout is implemented in the small-CTA forward kernel (unset GAMER_ATTN_FWD_WS)");
     if (!use_ws) {
         switch (kind) {
             case 0: return launch_fwd_small<0>(tq, tk, tv, to, p, stream);
@@ -1449,7 +1521,8 @@ long long attn_tc_bwd_ws_bytes(int B, int L, int n_q) { return bwd_layout(B, L, 
 
 int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv, int kind, int P,
                 const int* am, const int* act, const int* sess, float scale, const void* o, const void* d_o, long long ld_o,
-                const float* lse, void* ws, void* dq, void* dk, void* dv, long long ld_d, cudaStream_t stream) {
+                const float* lse, void* ws, void* dq, void* dk, void* dv, long long ld_d, const gamer_dropout_t* drop,
+                cudaStream_t stream) {
     const BwdLayout bl = bwd_layout(B, L, n_q);
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     if (int e = build_meta(kind, am, act, sess, B, L, w8, bl.ml, stream)) return e;
@@ -1484,6 +1557,7 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     p.lse_p = lse_p; p.dsum_p = dsum; p.uni_bits = uni;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.inv_L = 1.0f / (float)L; p.dq_acc = acc;
     p.tr = g_trace;
+    p.drop = make_drop(drop, 8);
     int e;
     switch (kind) {
         case 0: e = launch_bwd<0>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;

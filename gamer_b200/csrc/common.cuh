@@ -86,13 +86,40 @@ __device__ __forceinline__ bf16x8 float_to_bf16x8(const float* f) {
     return v;
 }
 
-// Philox4x32-10 counter RNG (dropout masks): deterministic in (seed, offset, index)
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                            uint32_t k1) {
+// ---------------------------------------------------------------------------------------------------------
+// Dropout (nn.Dropout on the residual branches / inside the experts, SDPA dropout_p on the attention probabilities:
+// Qwen3Multi/model.py:139,217,235,241, Qwen3Moe/FFN.py:26).  Masks come from the counter-based Philox4x32-7 generator
+// keyed on (seed, step offset) and indexed by (site, row, column), so the backward regenerates them instead of storing
+// them.  Hidden-state sites use 16 random bits per element, the attention probabilities 8 (one Philox call covers 16
+// keys); `scale` is the reciprocal of the realised keep probability, so E[dropout(x)] = x exactly.
+// ---------------------------------------------------------------------------------------------------------
+struct DropParams {
+    uint32_t k0, k1;   // Philox key: seed low word, seed high word ^ step offset
+    uint32_t site;     // which dropout call of the step (layer * 8 + kind)
+    uint32_t thresh;   // drop when the element's random value < thresh (0 = dropout off)
+    float scale;       // 1 / keep probability
+};
+
+static inline DropParams make_drop(const gamer_dropout_t* d, int bits) {
+    DropParams r{0u, 0u, 0u, 0u, 1.0f};
+    if (d == nullptr || !(d->p > 0.0f)) return r;
+    const uint32_t full = 1u << bits;
+    uint32_t t = (uint32_t)((double)d->p * (double)full);
+    if (t >= full) t = full - 1;
+    r.k0 = (uint32_t)(d->seed & 0xffffffffull);
+    r.k1 = (uint32_t)(d->seed >> 32) ^ d->offset;
+    r.site = d->site;
+    r.thresh = t;
+    r.scale = (float)((double)full / (double)(full - t));
+    return r;
+}
+
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;
@@ -101,4 +128,30 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
         k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+
+constexpr uint32_t DROP_HIDDEN_TAG = 0x64726f70u;  // counter word 3 of the hidden-state sites (attention uses the site id)
+
+// keep bits of the 8 columns [8*col8, 8*col8+8) of hidden row `row`: bit e set = element e is kept
+__device__ __forceinline__ uint32_t drop_keep8(const DropParams& d, uint32_t row, uint32_t col8) {
+    const uint4 r = philox4x32_7(col8, row, d.site, DROP_HIDDEN_TAG, d.k0, d.k1);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        keep |= ((w[q] & 0xffffu) >= d.thresh ? 1u : 0u) << (2 * q);
+        keep |= ((w[q] >> 16) >= d.thresh ? 1u : 0u) << (2 * q + 1);
+    }
+    return keep;
+}
+// in-place dropout of 8 consecutive fp32 values
+__device__ __forceinline__ void drop_apply8(const DropParams& d, uint32_t row, uint32_t col8, float* v) {
+    const uint32_t keep = drop_keep8(d, row, col8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * d.scale : 0.f;
+}
+// attention probabilities: random bytes of the 16 keys [16*jb, 16*jb+16) of query row i of (sequence, head) bh; key
+// 16*jb+e <-> byte (e & 3) of word (e >> 2); kept iff byte >= thresh
+__device__ __forceinline__ uint4 drop_attn16(const DropParams& d, uint32_t bh, uint32_t i, uint32_t jb) {
+    return philox4x32_7(jb, i, bh, d.site, d.k0, d.k1);
 }

@@ -9,9 +9,9 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-// gu: [R, 2*I] (gate | up), act: [R, I]
+// gu: [R, 2*I] (gate | up), act: [R, I] = dropout(silu(gate) * up); the mask row is row_ids[r] (token row) when given
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, bf16* __restrict__ act, long long ld_act,
-                                  long long R, int I) {
+                                  long long R, int I, const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -22,12 +22,17 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = g[k] * sigmoidf_(g[k]) * u[k];
+        if (dp.thresh) {
+            const long long mr = row_ids ? (long long)row_ids[r] : r;
+            if (mr >= 0) drop_apply8(dp, (uint32_t)mr, (uint32_t)(c >> 3), o);
+        }
         *reinterpret_cast<bf16x8*>(act + r * ld_act + c) = float_to_bf16x8(o);
     }
 }
 
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, const bf16* __restrict__ dact,
-                                  long long ld_dact, bf16* __restrict__ dgu, long long ld_dgu, long long R, int I) {
+                                  long long ld_dact, bf16* __restrict__ dgu, long long ld_dgu, long long R, int I,
+                                  const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -37,6 +42,10 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dact + r * ld_dact + c), d);
+        if (dp.thresh) {
+            const long long mr = row_ids ? (long long)row_ids[r] : r;
+            if (mr >= 0) drop_apply8(dp, (uint32_t)mr, (uint32_t)(c >> 3), d);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float s = sigmoidf_(g[k]);
@@ -48,10 +57,10 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
     }
 }
 
-// out = x + y * silu(g)      (all [R, W]; g has its own row stride: it lives inside the fused projection buffer)
+// out = x + dropout(y * silu(g))   (all [R, W]; g has its own row stride: it lives inside the fused projection buffer)
 __global__ void gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ out, long long R,
-                                         int W) {
+                                         int W, DropParams dp) {
     const int vec_per_row = W / 8;
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -62,15 +71,18 @@ __global__ void gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16*
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(g + r * ld_g + c), gf);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = xf[k] + yf[k] * gf[k] * sigmoidf_(gf[k]);
+        for (int k = 0; k < 8; ++k) o[k] = yf[k] * gf[k] * sigmoidf_(gf[k]);
+        if (dp.thresh) drop_apply8(dp, (uint32_t)r, (uint32_t)(c >> 3), o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += xf[k];
         *reinterpret_cast<bf16x8*>(out + r * W + c) = float_to_bf16x8(o);
     }
 }
 
-// dy = dout * silu(g);  dg = dout * y * silu'(g)
+// dz = dropout_mask * dout;  dy = dz * silu(g);  dg = dz * y * silu'(g)
 __global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y,
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ dy,
-                                         bf16* __restrict__ dg, long long ld_dg, long long R, int W) {
+                                         bf16* __restrict__ dg, long long ld_dg, long long R, int W, DropParams dp) {
     const int vec_per_row = W / 8;
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -80,6 +92,7 @@ __global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + r * W + c), d);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(g + r * ld_g + c), gf);
+        if (dp.thresh) drop_apply8(dp, (uint32_t)r, (uint32_t)(c >> 3), d);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float s = sigmoidf_(gf[k]);
@@ -91,20 +104,28 @@ __global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf
     }
 }
 
-// dst[r, :] = rows[r] >= 0 ? src[rows[r], :] : 0
+// dst[r, :] = rows[r] >= 0 ? dropout_mask[rows[r], :] * src[rows[r], :] : 0     (rows == nullptr: identity)
 __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long ld_src, const int* __restrict__ rows,
                                    const int* __restrict__ n_rows_dev, long long n_rows_max, bf16* __restrict__ dst,
-                                   long long ld_dst, int W) {
+                                   long long ld_dst, int W, DropParams dp) {
     const int vec_per_row = W / 8;
     const long long n_rows = n_rows_dev ? min((long long)*n_rows_dev, n_rows_max) : n_rows_max;
     const long long total = n_rows * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row;
         const int c = (int)(i % vec_per_row) * 8;
-        const int sr = rows[r];
+        const long long sr = rows ? (long long)rows[r] : r;
         bf16x8 v;
         v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
-        if (sr >= 0) v = *reinterpret_cast<const bf16x8*>(src + (long long)sr * ld_src + c);
+        if (sr >= 0) {
+            v = *reinterpret_cast<const bf16x8*>(src + sr * ld_src + c);
+            if (dp.thresh) {
+                float f[8];
+                bf16x8_to_float(v, f);
+                drop_apply8(dp, (uint32_t)sr, (uint32_t)(c >> 3), f);
+                v = float_to_bf16x8(f);
+            }
+        }
         *reinterpret_cast<bf16x8*>(dst + r * ld_dst + c) = v;
     }
 }
@@ -151,54 +172,70 @@ inline int grid_for(long long total, int threads) {
 }  // namespace
 
 extern "C" int gamer_swiglu_fwd(const void* gu, long long ld_gu, void* act, long long ld_act, long long R, int I,
-                                cudaStream_t stream) {
+                                const int* row_ids, const gamer_dropout_t* drop, cudaStream_t stream) {
     GAMER_REQUIRE(I % 8 == 0, "intermediate size must be a multiple of 8");
     if (R == 0) return 0;
     swiglu_fwd_kernel<<<grid_for(R * (I / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(gu), ld_gu,
-                                                                      reinterpret_cast<bf16*>(act), ld_act, R, I);
+                                                                      reinterpret_cast<bf16*>(act), ld_act, R, I,
+                                                                      row_ids, make_drop(drop, 16));
     GAMER_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gamer_swiglu_bwd(const void* gu, long long ld_gu, const void* dact, long long ld_dact, void* dgu,
-                                long long ld_dgu, long long R, int I, cudaStream_t stream) {
+                                long long ld_dgu, long long R, int I, const int* row_ids,
+                                const gamer_dropout_t* drop, cudaStream_t stream) {
     GAMER_REQUIRE(I % 8 == 0, "intermediate size must be a multiple of 8");
     if (R == 0) return 0;
     swiglu_bwd_kernel<<<grid_for(R * (I / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(gu), ld_gu, reinterpret_cast<const bf16*>(dact), ld_dact,
-        reinterpret_cast<bf16*>(dgu), ld_dgu, R, I);
+        reinterpret_cast<bf16*>(dgu), ld_dgu, R, I, row_ids, make_drop(drop, 16));
     GAMER_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gamer_gate_residual_fwd(const void* x, const void* y, const void* g, long long ld_g, void* out,
-                                       long long R, int W, cudaStream_t stream) {
+                                       long long R, int W, const gamer_dropout_t* drop, cudaStream_t stream) {
     GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
     if (R == 0) return 0;
     gate_residual_fwd_kernel<<<grid_for(R * (W / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(g), ld_g,
-        reinterpret_cast<bf16*>(out), R, W);
+        reinterpret_cast<bf16*>(out), R, W, make_drop(drop, 16));
     GAMER_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gamer_gate_residual_bwd(const void* dout, const void* y, const void* g, long long ld_g, void* dy,
-                                       void* dg, long long ld_dg, long long R, int W, cudaStream_t stream) {
+                                       void* dg, long long ld_dg, long long R, int W, const gamer_dropout_t* drop,
+                                       cudaStream_t stream) {
     GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
     if (R == 0) return 0;
     gate_residual_bwd_kernel<<<grid_for(R * (W / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(g), ld_g,
-        reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dg), ld_dg, R, W);
+        reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dg), ld_dg, R, W, make_drop(drop, 16));
     GAMER_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gamer_gather_rows(const void* src, long long ld_src, const int* rows, const int* n_rows_dev,
-                                 long long n_rows_max, void* dst, long long ld_dst, int W, cudaStream_t stream) {
+                                 long long n_rows_max, void* dst, long long ld_dst, int W, const gamer_dropout_t* drop,
+                                 cudaStream_t stream) {
     GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
     if (n_rows_max == 0) return 0;
     gather_rows_kernel<<<grid_for(n_rows_max * (W / 8), 256), 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows_dev, n_rows_max, reinterpret_cast<bf16*>(dst), ld_dst, W);
+        reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows_dev, n_rows_max, reinterpret_cast<bf16*>(dst), ld_dst, W,
+        make_drop(drop, 16));
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_dropout_apply(const void* in, void* out, long long R, int W, const gamer_dropout_t* drop,
+                                   cudaStream_t stream) {
+    GAMER_REQUIRE(W % 8 == 0, "width must be a multiple of 8");
+    if (R == 0) return 0;
+    gather_rows_kernel<<<grid_for(R * (W / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), W, nullptr,
+                                                                       nullptr, R, reinterpret_cast<bf16*>(out), W, W,
+                                                                       make_drop(drop, 16));
     GAMER_LAUNCH_CHECK();
     return 0;
 }

@@ -30,6 +30,7 @@ struct GemmParams {
     long long ldr;
     const int* row_map;  // out row for A-row r (-1: skip); nullptr => identity
     float alpha;
+    DropParams drop;     // dropout of alpha * A B^T before the residual add (mask indexed by output row, column)
 };
 
 constexpr int BLOCK_N = 128;
@@ -234,6 +235,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float v[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]) * p.alpha;
+                            if (p.drop.thresh)
+                                drop_apply8(p.drop, (uint32_t)(row0 + trow), (uint32_t)((n_blk * BLOCK_N + c * 32 + q * 8) >> 3), v);
                             if (has_resid) {
                                 bf16x8 rv;
                                 lds128(addr, rv.u[0], rv.u[1], rv.u[2], rv.u[3]);
@@ -282,6 +285,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                        if (p.drop.thresh) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) drop_apply8(p.drop, (uint32_t)orow, (uint32_t)((col0 >> 3) + q), v + 8 * q);
+                        }
                         const bool full = (col0 + 32 <= p.N);
                         if (p.resid != nullptr) {
                             const bf16* rp = p.resid + orow * p.ldr + col0;
@@ -637,7 +644,7 @@ int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const void* B, long long ldb, int n_groups,
                                   int N, int K, const int* seg_off, void* C, long long ldc, int c_is_f32,
                                   const void* resid, long long ldr, const int* row_map, float alpha,
-                                  cudaStream_t stream) {
+                                  const gamer_dropout_t* drop, cudaStream_t stream) {
     if (rows <= 0) return 0;
     GAMER_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, "n_groups=%d out of range", n_groups);
     GAMER_REQUIRE(n_groups == 1 || seg_off != nullptr, "grouped GEMM needs seg_off");
@@ -648,7 +655,9 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
     CUtensorMap tmA, tmB, tmC, tmR;
     if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;
     if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, BLOCK_N)) return e;
-    GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha};
+    GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha,
+                 make_drop(drop, 16)};
+    GAMER_REQUIRE(p.drop.thresh == 0 || !c_is_f32, "dropout epilogue is implemented for bf16 outputs");
     // staged (TMA-store) epilogue whenever output rows are the A rows; fp32 outputs carry no residual in this code base
     const bool staged = row_map == nullptr && !(c_is_f32 && resid != nullptr);
     if (!staged) {

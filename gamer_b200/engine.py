@@ -223,6 +223,32 @@ def behaviour_lut(arch: Arch, device):
     return lut.to(device)
 
 
+# dropout call sites within one layer (gamer_dropout_t.site = layer * 8 + kind)
+SITE_SELF_P, SITE_SELF_OUT, SITE_CROSS_P, SITE_CROSS_OUT, SITE_FFN_INNER, SITE_FFN_OUT = range(6)
+
+
+@dataclass
+class DropCtx:
+    """Training-mode dropout of one forward pass (Qwen3Multi/model.py:139,177,217,235,241; Qwen3Moe/FFN.py:23-26):
+    `p_hidden` = config.dropout_rate on the three residual branches and inside the experts, `p_attn` =
+    config.attention_dropout on the attention probabilities.  (seed, offset) key the Philox masks; the backward is
+    handed the same context and regenerates them."""
+    seed: int
+    offset: int
+    p_hidden: float
+    p_attn: float
+
+    def site(self, layer: int, kind: int):
+        p = self.p_attn if kind in (SITE_SELF_P, SITE_CROSS_P) else self.p_hidden
+        if p <= 0.0:
+            return None
+        return K.Dropout(self.seed & 0xFFFFFFFFFFFFFFFF, self.offset & 0xFFFFFFFF, layer * 8 + kind, float(p))
+
+
+def _site(drop, layer, kind):
+    return None if drop is None else drop.site(layer, kind)
+
+
 @dataclass
 class BatchMeta:
     """Per-batch integer side inputs, converted once to the int32 arrays the kernels read."""
@@ -259,8 +285,9 @@ def make_meta(arch: Arch, input_ids, attention_mask, actions, session_ids, exten
 # ======================================================================================================================
 # forward
 # ======================================================================================================================
-def _attention_fwd(arch, meta, x, norm_w, w_qkv, qn, kn, w_o, kind, tabs, act_idx=None, embs=None, gated=False):
-    """pre-norm attention sub-block.  Returns (x_out, saved)."""
+def _attention_fwd(arch, meta, x, norm_w, w_qkv, qn, kn, w_o, kind, tabs, act_idx=None, embs=None, gated=False,
+                   drop_p=None, drop_out=None):
+    """pre-norm attention sub-block: x + dropout(attention(norm(x))).  Returns (x_out, saved)."""
     M = x.shape[0]
     h, rstd = K.rmsnorm_fwd(x, norm_w, arch.eps)
     n_proj = w_qkv.shape[0]
@@ -269,17 +296,18 @@ def _attention_fwd(arch, meta, x, norm_w, w_qkv, qn, kn, w_o, kind, tabs, act_id
     rot = K.qk_norm_rope_fwd(raw, meta.L, arch.n_q, arch.n_kv, arch.head_dim, tabs[0], tabs[1], qn, kn, arch.eps,
                              pos_ids=meta.rope_pos, q_emb=qe, k_emb=ke, v_emb=ve, act_idx=act_idx)
     o, lse, vmean = K.attn_fwd(rot, meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P, meta.am, meta.act,
-                               meta.sess, arch.head_dim ** -0.5)
+                               meta.sess, arch.head_dim ** -0.5, drop=drop_p)
     if gated:
         y = K.gemm_tn(o, w_o, arch.hidden)
-        x_out = K.gate_residual_fwd(x, y, raw[:, arch.qkv_w:])
+        x_out = K.gate_residual_fwd(x, y, raw[:, arch.qkv_w:], drop=drop_out)
     else:
         y = None
-        x_out = K.gemm_tn(o, w_o, arch.hidden, resid=x)
+        x_out = K.gemm_tn(o, w_o, arch.hidden, resid=x, drop=drop_out)
     return x_out, dict(x=x, rstd=rstd, h=h, raw=raw, rot=rot, o=o, lse=lse, y=y, vmean=vmean)
 
 
-def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save: bool, kv_sink: list | None = None):
+def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save: bool, kv_sink: list | None = None,
+                  drop: DropCtx | None = None):
     """-> (final normed hidden [M,H] bf16, ctx).  ctx holds what the backward needs when save=True.  `kv_sink` (decode
     prefill) receives per layer {"self": (rot, vmean), "cross": (rot, vmean)} — the rotated q|k|v buffers double as the
     prompt K/V cache."""
@@ -298,12 +326,14 @@ def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save:
     for l in range(arch.n_layers):
         d = pack.layers[l]
         saved = {}
-        x, s_self = _attention_fwd(arch, meta, x, d["in_norm"], d["w_qkv"], d["qn"], d["kn"], d["w_o"], k_self, tabs)
+        x, s_self = _attention_fwd(arch, meta, x, d["in_norm"], d["w_qkv"], d["qn"], d["kn"], d["w_o"], k_self, tabs,
+                                   drop_p=_site(drop, l, SITE_SELF_P), drop_out=_site(drop, l, SITE_SELF_OUT))
         saved["self"] = s_self
         if l in arch.cross:
             x, s_cross = _attention_fwd(arch, meta, x, d["ps_norm"], d["c_w_qkvg"], d["c_qn"], d["c_kn"], d["c_w_o"],
                                         k_cross, tabs, act_idx=act_idx, embs=(d["c_qe"], d["c_ke"], d["c_ve"]),
-                                        gated=True)
+                                        gated=True, drop_p=_site(drop, l, SITE_CROSS_P),
+                                        drop_out=_site(drop, l, SITE_CROSS_OUT))
             saved["cross"] = s_cross
         # routed FFN
         sparse = l in arch.sparse
@@ -314,16 +344,16 @@ def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save:
             _, rstd = K.rmsnorm_fwd(x, d["post_norm"], arch.eps, out=hp, row_map=perm,
                                     cat_table=d.get("beh_emb"), cat_idx=beh_idx if inject else None)
             gu = K.gemm_tn(hp, d["w_gu"], 2 * arch.inter, rows=Mp, n_groups=arch.n_exp, seg_off=seg)
-            a = K.swiglu_fwd(gu, arch.inter)
+            a = K.swiglu_fwd(gu, arch.inter, row_ids=rows, drop=_site(drop, l, SITE_FFN_INNER))
             x_out = torch.empty_like(x)
             K.gemm_tn(a, d["w_d"], arch.hidden, rows=Mp, n_groups=arch.n_exp, seg_off=seg, out=x_out, resid=x,
-                      row_map=rows)
+                      row_map=rows, drop=_site(drop, l, SITE_FFN_OUT))
         else:
             hp, rstd = K.rmsnorm_fwd(x, d["post_norm"], arch.eps, cat_table=d.get("beh_emb"),
                                      cat_idx=beh_idx if inject else None)
             gu = K.gemm_tn(hp, d["w_gu"], 2 * arch.inter)
-            a = K.swiglu_fwd(gu, arch.inter)
-            x_out = K.gemm_tn(a, d["w_d"], arch.hidden, resid=x)
+            a = K.swiglu_fwd(gu, arch.inter, drop=_site(drop, l, SITE_FFN_INNER))
+            x_out = K.gemm_tn(a, d["w_d"], arch.hidden, resid=x, drop=_site(drop, l, SITE_FFN_OUT))
         saved["ffn"] = dict(x=x, rstd=rstd, hp=hp, gu=gu, a=a)
         x = x_out
         if save:
@@ -366,21 +396,21 @@ def lm_head_loss(arch: Arch, pack: Pack, hidden, shifted, inv_norm, temperature)
 # backward
 # ======================================================================================================================
 def _attention_bwd(arch, meta, s, dx_out, norm_w, w_qkv_t, qn, kn, w_o_t, kind, tabs, G, names, act_idx=None, embs=None,
-                   gated=False):
+                   gated=False, drop_p=None, drop_out=None):
     """Returns dx (grad wrt the sub-block input).  Parameter grads are accumulated into G[name] (fp32)."""
     dev = dx_out.device
     M = dx_out.shape[0]
     n_proj = w_qkv_t.shape[1]
     draw = torch.empty(M, n_proj, dtype=BF16, device=dev)
     if gated:
-        dy = K.gate_residual_bwd(dx_out, s["y"], s["raw"][:, arch.qkv_w:], draw[:, arch.qkv_w:])
+        dy = K.gate_residual_bwd(dx_out, s["y"], s["raw"][:, arch.qkv_w:], draw[:, arch.qkv_w:], drop=drop_out)
     else:
-        dy = dx_out
+        dy = dx_out if drop_out is None else K.dropout_apply(dx_out, drop_out)
     d_o = K.gemm_tn(dy, w_o_t, arch.q_w)
     K.gemm_wgrad(dy, s["o"], arch.hidden, arch.q_w, G[names["o"]].view(1, arch.hidden, arch.q_w))
     drot = torch.empty(M, arch.qkv_w, dtype=BF16, device=dev)
     K.attn_bwd(s["rot"], s["o"], d_o, s["lse"], meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P,
-               meta.am, meta.act, meta.sess, arch.head_dim ** -0.5, drot)
+               meta.am, meta.act, meta.sess, arch.head_dim ** -0.5, drot, drop=drop_p)
     qe, ke, ve = embs if embs is not None else (None, None, None)
     K.qk_norm_rope_bwd(s["raw"], drot, draw, meta.L, arch.n_q, arch.n_kv, arch.head_dim, tabs[0], tabs[1], qn, kn,
                        arch.eps, G[names["qn"]], G[names["kn"]], pos_ids=meta.rope_pos, q_emb=qe, k_emb=ke, v_emb=ve,
@@ -391,7 +421,8 @@ def _attention_bwd(arch, meta, s, dx_out, norm_w, w_qkv_t, qn, kn, w_o_t, kind, 
     return K.rmsnorm_bwd(s["x"], norm_w, s["rstd"], arch.eps, dh, G[names["norm"]], dres=dx_out)
 
 
-def backward_stack(arch: Arch, pack: Pack, meta: BatchMeta, ctx, d_hidden, G: dict, on_layer_done=None):
+def backward_stack(arch: Arch, pack: Pack, meta: BatchMeta, ctx, d_hidden, G: dict, on_layer_done=None,
+                   drop: DropCtx | None = None):
     """d_hidden: grad wrt the final normed hidden [M,H] bf16.  G: fused fp32 gradient buffers (see `grad_buffers`).
     Returns dx0 (grad wrt the embedding output)."""
     tabs = ctx["tabs"]
@@ -411,14 +442,16 @@ def backward_stack(arch: Arch, pack: Pack, meta: BatchMeta, ctx, d_hidden, G: di
         E = arch.n_exp if sparse else 1
         if sparse:
             Mp = s["hp"].shape[0]
-            dxp = K.gather_rows(dx, ctx["rows"], Mp)
+            dxp = K.gather_rows(dx, ctx["rows"], Mp, drop=_site(drop, l, SITE_FFN_OUT))
             seg = ctx["seg"]
         else:
             Mp = dx.shape[0]
-            dxp, seg = dx, None
+            d_out = _site(drop, l, SITE_FFN_OUT)
+            dxp, seg = (dx if d_out is None else K.dropout_apply(dx, d_out)), None
         da = K.gemm_tn(dxp, d["w_d_t"], arch.inter, rows=Mp, n_groups=E, seg_off=seg)
         K.gemm_wgrad(dxp, s["a"], arch.hidden, arch.inter, G[p + "w_d"], rows=Mp, n_groups=E, seg_off=seg)
-        dgu = K.swiglu_bwd(s["gu"], da, arch.inter)
+        dgu = K.swiglu_bwd(s["gu"], da, arch.inter, row_ids=ctx["rows"] if sparse else None,
+                           drop=_site(drop, l, SITE_FFN_INNER))
         dhp = K.gemm_tn(dgu, d["w_gu_t"], Kf, rows=Mp, n_groups=E, seg_off=seg)
         K.gemm_wgrad(dgu, s["hp"], 2 * arch.inter, Kf, G[p + "w_gu"], rows=Mp, n_groups=E, seg_off=seg)
         dx = K.rmsnorm_bwd(s["x"], d["post_norm"], s["rstd"], arch.eps, dhp, G[p + "post_norm"],
@@ -430,10 +463,12 @@ def backward_stack(arch: Arch, pack: Pack, meta: BatchMeta, ctx, d_hidden, G: di
                          qe=p + "c_qe", ke=p + "c_ke", ve=p + "c_ve")
             dx = _attention_bwd(arch, meta, saved["cross"], dx, d["ps_norm"], d["c_w_qkvg_t"], d["c_qn"], d["c_kn"],
                                 d["c_w_o_t"], k_cross, tabs, G, names, act_idx=ctx["act_idx"],
-                                embs=(d["c_qe"], d["c_ke"], d["c_ve"]), gated=True)
+                                embs=(d["c_qe"], d["c_ke"], d["c_ve"]), gated=True,
+                                drop_p=_site(drop, l, SITE_CROSS_P), drop_out=_site(drop, l, SITE_CROSS_OUT))
         names = dict(o=p + "w_o", qkv=p + "w_qkv", qn=p + "qn", kn=p + "kn", norm=p + "in_norm")
         dx = _attention_bwd(arch, meta, saved["self"], dx, d["in_norm"], d["w_qkv_t"], d["qn"], d["kn"], d["w_o_t"],
-                            k_self, tabs, G, names)
+                            k_self, tabs, G, names, drop_p=_site(drop, l, SITE_SELF_P),
+                            drop_out=_site(drop, l, SITE_SELF_OUT))
         saved.clear()
         if on_layer_done is not None:
             on_layer_done(l)
@@ -577,13 +612,13 @@ def lm_head_backward(arch: Arch, pack: Pack, hidden, shifted, scale_dev, tempera
     return d_hidden
 
 
-def loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature):
+def loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, drop: DropCtx | None = None):
     """Forward of the training step.  Returns (loss, state for `loss_backward`)."""
-    hidden, saved = forward_stack(arch, pack, input_ids, meta, lut, save=True)
+    hidden, saved = forward_stack(arch, pack, input_ids, meta, lut, save=True, drop=drop)
     loss = lm_head_loss(arch, pack, hidden, shifted, inv_norm, temperature)
     sort_buf = K.embed_sort(input_ids.view(-1), arch.vocab, arch.pad)
     return loss, dict(saved=saved, hidden=hidden, shifted=shifted, inv_norm=inv_norm, temperature=temperature,
-                      sort_buf=sort_buf, meta=meta)
+                      sort_buf=sort_buf, meta=meta, drop=drop)
 
 
 def loss_backward(arch, pack, st, grad_out, G, on_layer_done=None):
@@ -591,7 +626,8 @@ def loss_backward(arch, pack, st, grad_out, G, on_layer_done=None):
     scale = (grad_out.float().reshape(()) * st["inv_norm"].view(())).reshape(1).contiguous()
     d_hidden = lm_head_backward(arch, pack, st["hidden"], st["shifted"], scale, st["temperature"],
                                 G["model.embed_tokens.weight"])
-    dx0 = backward_stack(arch, pack, st["meta"], st["saved"], d_hidden, G, on_layer_done=on_layer_done)
+    dx0 = backward_stack(arch, pack, st["meta"], st["saved"], d_hidden, G, on_layer_done=on_layer_done,
+                         drop=st.get("drop"))
     K.embed_bwd(dx0, arch.vocab, st["sort_buf"], G["model.embed_tokens.weight"])
     if on_layer_done is not None:
         on_layer_done(-1)
@@ -603,8 +639,8 @@ class DecoderLossFunction(torch.autograd.Function):
     `param_names(arch)` order; backward returns their gradients (views of one flat fused buffer)."""
 
     @staticmethod
-    def forward(ctx, arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, hooks, *params):
-        loss, st = loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature)
+    def forward(ctx, arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, hooks, drop, *params):
+        loss, st = loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, drop=drop)
         ctx.arch, ctx.pack, ctx.st, ctx.hooks = arch, pack, st, hooks
         return loss
 
@@ -617,4 +653,4 @@ class DecoderLossFunction(torch.autograd.Function):
         named = unfuse_grads(arch, G)
         grads = tuple(named[n] for n in param_names(arch))
         ctx.st = None
-        return (None,) * 9 + grads
+        return (None,) * 10 + grads

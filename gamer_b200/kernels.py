@@ -3,6 +3,8 @@ tensors out.  PyTorch is used for device memory and streams only; all arithmetic
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from ._cabi import call, lib, ptr
@@ -13,6 +15,16 @@ MASK_CAUSAL, MASK_MULTI_CROSS, MASK_SESSION, MASK_SESSION_CROSS = 0, 1, 2, 3
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+class Dropout(ctypes.Structure):
+    """gamer_dropout_t (include/gamer_b200.h): one dropout call site of a forward pass; the backward passes the same
+    struct and the kernels regenerate the Philox mask."""
+    _fields_ = [("seed", ctypes.c_ulonglong), ("offset", ctypes.c_uint), ("site", ctypes.c_uint), ("p", ctypes.c_float)]
+
+
+def _drop(d):
+    return None if d is None else ctypes.addressof(d)
 
 
 def _req(t: torch.Tensor, dtype=None):
@@ -118,8 +130,8 @@ def qk_norm_rope_bwd(raw, dout, draw, L, n_q, n_kv, hd, cos_tab, sin_tab, qn_w, 
 
 # ------------------------------------------------------------------------------------------------ K4/K7
 def gemm_tn(a, b, N, K=None, rows=None, n_groups=1, seg_off=None, out=None, out_f32=False, resid=None, row_map=None,
-            alpha=1.0, out_rows=None):
-    """C = alpha * A @ B_g^T (+ resid).  a: bf16 [rows, >=K] (row stride a.stride(0)); b: bf16 [n_groups*N, >=K]."""
+            alpha=1.0, out_rows=None, drop=None):
+    """C = dropout(alpha * A @ B_g^T) (+ resid).  a: bf16 [rows, >=K] (row stride a.stride(0)); b: bf16 [n_groups*N, >=K]."""
     rows = a.shape[0] if rows is None else rows
     K = a.shape[1] if K is None else K
     if out is None:
@@ -127,7 +139,7 @@ def gemm_tn(a, b, N, K=None, rows=None, n_groups=1, seg_off=None, out=None, out_
                           device=a.device)
     call("gamer_gemm_bf16_tn", ptr(a), a.stride(0), rows, ptr(b), b.stride(0), n_groups, N, K, ptr(seg_off), ptr(out),
          out.stride(0), 1 if out.dtype == torch.float32 else 0, ptr(resid), 0 if resid is None else resid.stride(0),
-         ptr(row_map), float(alpha), _stream(),
+         ptr(row_map), float(alpha), _drop(drop), _stream(),
          work=(2 * rows * N * K, rows * K * 2 + n_groups * N * K * 2 + rows * N * out.element_size()))
     return out
 
@@ -148,7 +160,7 @@ def ref_gemm_tn(a, b, N, K):
 
 
 # ------------------------------------------------------------------------------------------------ K6
-def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
+def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, drop=None):
     """qkv bf16 [B*L, ld]: q cols [0, n_q*hd), k next n_kv*hd, v next n_kv*hd.
     -> (o [B*L, n_q*hd], lse [B,n_q,L], vmean fp32 [B, n_kv, hd] = mean of all L value rows)."""
     dev = qkv.device
@@ -160,12 +172,12 @@ def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale):
     k = q + n_q * hd * esz
     v = k + n_kv * hd * esz
     call("gamer_attn_fwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
-         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _stream(),
+         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _drop(drop), _stream(),
          work=(4 * hd * n_q * B * L * (L + 1) // 2, B * L * (2 * n_q + 2 * n_kv) * hd * 2))   # causal pair count (§8d)
     return o, lse, ws[: B * n_kv * hd * 4].view(torch.float32).view(B, n_kv, hd)
 
 
-def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv):
+def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv, drop=None):
     dev = qkv.device
     ws = torch.empty(lib().gamer_attn_bwd_workspace_bytes(B, L, n_q), dtype=torch.uint8, device=dev)
     esz = 2
@@ -176,46 +188,56 @@ def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scal
     dk = dq + n_q * hd * esz
     dv = dk + n_kv * hd * esz
     call("gamer_attn_bwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
-         float(scale), ptr(o), ptr(d_o), o.stride(0), ptr(lse), ptr(ws), dq, dk, dv, dqkv.stride(0), _stream(),
+         float(scale), ptr(o), ptr(d_o), o.stride(0), ptr(lse), ptr(ws), dq, dk, dv, dqkv.stride(0), _drop(drop),
+         _stream(),
          work=(10 * hd * n_q * B * L * (L + 1) // 2, B * L * (4 * n_q + 4 * n_kv) * hd * 2))
     return dqkv
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
-def swiglu_fwd(gu, I, rows=None):
+def swiglu_fwd(gu, I, rows=None, row_ids=None, drop=None):
+    """act = dropout(silu(gate) * up); row_ids maps rows of the expert-permuted space to token rows (mask index)."""
     R = gu.shape[0] if rows is None else rows
     act = torch.empty(gu.shape[0], I, dtype=BF16, device=gu.device)
-    call("gamer_swiglu_fwd", ptr(gu), gu.stride(0), ptr(act), act.stride(0), R, I, _stream())
+    call("gamer_swiglu_fwd", ptr(gu), gu.stride(0), ptr(act), act.stride(0), R, I, ptr(row_ids), _drop(drop), _stream())
     return act
 
 
-def swiglu_bwd(gu, dact, I):
+def swiglu_bwd(gu, dact, I, row_ids=None, drop=None):
     dgu = torch.empty_like(gu)
     call("gamer_swiglu_bwd", ptr(gu), gu.stride(0), ptr(dact), dact.stride(0), ptr(dgu), dgu.stride(0), gu.shape[0], I,
-         _stream())
+         ptr(row_ids), _drop(drop), _stream())
     return dgu
 
 
-def gate_residual_fwd(x, y, g_view):
+def gate_residual_fwd(x, y, g_view, drop=None):
+    """out = x + dropout(y * silu(g))."""
     out = torch.empty_like(x)
     call("gamer_gate_residual_fwd", ptr(x), ptr(y), ptr(g_view), g_view.stride(0), ptr(out), x.shape[0], x.shape[1],
-         _stream())
+         _drop(drop), _stream())
     return out
 
 
-def gate_residual_bwd(dout, y, g_view, dg_view):
+def gate_residual_bwd(dout, y, g_view, dg_view, drop=None):
     dy = torch.empty_like(dout)
     call("gamer_gate_residual_bwd", ptr(dout), ptr(y), ptr(g_view), g_view.stride(0), ptr(dy), ptr(dg_view),
-         dg_view.stride(0), dout.shape[0], dout.shape[1], _stream())
+         dg_view.stride(0), dout.shape[0], dout.shape[1], _drop(drop), _stream())
     return dy
 
 
-def gather_rows(src, rows, n_rows_max, width=None, n_rows_dev=None):
+def gather_rows(src, rows, n_rows_max, width=None, n_rows_dev=None, drop=None):
     W = src.shape[1] if width is None else width
     dst = torch.empty(n_rows_max, W, dtype=BF16, device=src.device)
     call("gamer_gather_rows", ptr(src), src.stride(0), ptr(rows), ptr(n_rows_dev), n_rows_max, ptr(dst), dst.stride(0),
-         W, _stream())
+         W, _drop(drop), _stream())
     return dst
+
+
+def dropout_apply(x, drop):
+    """dropout(x) with the mask of `drop` (x contiguous [R, W]); the backward of a dropout fused into a GEMM epilogue."""
+    out = torch.empty_like(x)
+    call("gamer_dropout_apply", ptr(x), ptr(out), x.shape[0], x.shape[1], _drop(drop), _stream())
+    return out
 
 
 def ce_fwd_bwd(logits, labels, V, inv_norm, grad_scale, dlogits=None, ignore_index=-100):

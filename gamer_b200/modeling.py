@@ -124,6 +124,8 @@ class _GamerCausalLM(PreTrainedModel):
         self._pack_key = None
         self._lut = None
         self.grad_hooks = {}
+        self._drop_seed = None          # None: derived from torch.initial_seed() and the rank at first use
+        self._drop_calls = 0
 
     # ---- HF plumbing ---------------------------------------------------------------------------------------------
     def _init_weights(self, module):
@@ -167,6 +169,25 @@ class _GamerCausalLM(PreTrainedModel):
         sd.setdefault("lm_head.weight", self.model.embed_tokens.weight)
         return sd
 
+    def set_dropout_seed(self, seed: int):
+        """Fix the Philox seed of the training-mode dropout masks (default: torch.initial_seed() mixed with the rank)."""
+        self._drop_seed = int(seed)
+        self._drop_calls = 0
+
+    def _next_drop(self):
+        """Dropout context of the next training-mode forward (nn.Dropout(config.dropout_rate) / SDPA
+        dropout_p=config.attention_dropout in the reference, Qwen3Multi/model.py:139,177); None in eval mode."""
+        p_h = float(getattr(self.config, "dropout_rate", 0.0) or 0.0)
+        p_a = float(getattr(self.config, "attention_dropout", 0.0) or 0.0)
+        if not self.training or (p_h <= 0.0 and p_a <= 0.0):
+            return None
+        if self._drop_seed is None:
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            self._drop_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03 * (rank + 1)) & (2 ** 64 - 1)
+        d = E.DropCtx(self._drop_seed, self._drop_calls, p_h, p_a)
+        self._drop_calls += 1
+        return d
+
     def _get_pack(self, arch):
         """bf16 operand pack, rebuilt whenever any master weight changed (optimizer step, load_state_dict)."""
         params = list(self.parameters())
@@ -203,20 +224,21 @@ class _GamerCausalLM(PreTrainedModel):
         num_items = kwargs.get("num_items_in_batch", None)
         want_grad = labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         loss, logits = None, None
+        drop = self._next_drop()
         if want_grad:
             shifted = E.shift_labels(labels)
             inv_norm = self._inv_norm(shifted, num_items)
             names = E.param_names(arch)
             W = self._named_weights()
             loss = E.DecoderLossFunction.apply(arch, pack, meta, lut, input_ids, shifted, inv_norm, float(self.temperature),
-                                               self.grad_hooks, *[W[n] for n in names])
+                                               self.grad_hooks, drop, *[W[n] for n in names])
             if getattr(self.config, "gamer_return_train_logits", False):
                 with torch.no_grad():
-                    hidden, _ = E.forward_stack(arch, pack, input_ids, meta, lut, save=False)
+                    hidden, _ = E.forward_stack(arch, pack, input_ids, meta, lut, save=False, drop=drop)
                     logits = E.lm_head_logits(arch, pack, hidden, 1.0 / self.temperature).view(B, L, -1)
         else:
             with torch.no_grad():
-                hidden, _ = E.forward_stack(arch, pack, input_ids, meta, lut, save=False)
+                hidden, _ = E.forward_stack(arch, pack, input_ids, meta, lut, save=False, drop=drop)
                 hidden = hidden.view(B, L, -1)
                 if isinstance(logits_to_keep, int) and logits_to_keep > 0:
                     hidden_k = hidden[:, -logits_to_keep:, :]

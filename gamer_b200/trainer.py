@@ -99,7 +99,8 @@ class NativeTrainer:
         meta = E.make_meta(a, ids, batch.get("attention_mask"), batch.get("actions"), batch.get("session_ids"),
                            batch.get("extended_session_ids"))
         shifted = E.shift_labels(batch["labels"])
-        loss, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature))
+        loss, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature),
+                                  drop=self.model._next_drop())
         one = torch.ones((), dtype=torch.float32, device=self.dev)
         E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=self._bucket_hook if last_micro else None)
         return loss

@@ -34,6 +34,19 @@ typedef struct CUstream_st* gamer_stream_t; /* == cudaStream_t */
 
 const char* gamer_last_error(void);
 
+/* Dropout of one call site (nn.Dropout(config.dropout_rate): Qwen3Multi/model.py:177,217,235,241, Qwen3Moe/FFN.py:23-26;
+ * SDPA dropout_p = config.attention_dropout: Qwen3Multi/model.py:139).  HOST struct; NULL or p <= 0 = no dropout
+ * (eval mode).  Masks are Philox4x32-7 bits indexed by (seed, offset, site, row, column) — the backward entry points
+ * take the same struct and regenerate them.  Hidden-state sites drop with probability floor(p*65536)/65536, attention
+ * probabilities with floor(p*256)/256; kept elements are scaled by the reciprocal of the realised keep probability. */
+typedef struct {
+    unsigned long long seed; /* generator seed (per rank) */
+    unsigned int offset;     /* advances once per forward pass (micro-batch) */
+    unsigned int site;       /* dropout call within the pass: layer * 8 + {0 self P, 1 self out, 2 cross P, 3 cross out,
+                                4 expert inner, 5 FFN out} */
+    float p;
+} gamer_dropout_t;
+
 /* ---- K1: embedding gather + router indices ------------------------------------------------------------------
  * replaces embed_tokens(input_ids) (Qwen3Multi/model.py:779) and Qwen3MultiDecoderRouter.forward
  * (Qwen3Multi/router.py:74-201; Qwen3Moe/router.py:74-154).  ids/ctx are int64 as the reference passes them.
@@ -79,7 +92,7 @@ int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const void* dout, 
  * grouped mode: seg_off[n_groups+1] (device) gives 128-aligned row segments, segment g uses weight slab g. */
 int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const void* B, long long ldb, int n_groups, int N, int K,
                        const int* seg_off, void* C, long long ldc, int c_is_f32, const void* resid, long long ldr,
-                       const int* row_map, float alpha, gamer_stream_t stream);
+                       const int* row_map, float alpha, const gamer_dropout_t* drop, gamer_stream_t stream);
 /* dW[g][i, j] += sum_r dY[r, i] * X[r, j]   (fp32 accumulate into dW [n_groups, N_out, K_in]) */
 int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* X, long long ldx, int rows, int N_out, int K_in,
                           int n_groups, const int* seg_off, float* dW, gamer_stream_t stream);
@@ -93,24 +106,32 @@ long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv);
 int gamer_attn_set_trace(void* buf, int cap);
 int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
-                   float scale, void* workspace, void* o, long long ld_o, float* lse, gamer_stream_t stream);
+                   float scale, void* workspace, void* o, long long ld_o, float* lse, const gamer_dropout_t* drop,
+                   gamer_stream_t stream);
 long long gamer_attn_bwd_workspace_bytes(int B, int L, int n_q);
 int gamer_attn_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
                    float scale, const void* o, const void* d_o, long long ld_o, const float* lse, void* workspace,
-                   void* dq, void* dk, void* dv, long long ld_d, gamer_stream_t stream);
+                   void* dq, void* dk, void* dv, long long ld_d, const gamer_dropout_t* drop, gamer_stream_t stream);
 
 /* ---- elementwise pieces --------------------------------------------------------------------------------------- */
+/* act = dropout(silu(gate) * up) (Qwen3Moe/FFN.py:26).  row_ids (may be NULL = identity) maps a row of the expert-
+ * permuted space to its token row (-1 = padding row): the dropout mask is indexed by token row. */
 int gamer_swiglu_fwd(const void* gu, long long ld_gu, void* act, long long ld_act, long long R, int I,
-                     gamer_stream_t stream);
+                     const int* row_ids, const gamer_dropout_t* drop, gamer_stream_t stream);
 int gamer_swiglu_bwd(const void* gu, long long ld_gu, const void* dact, long long ld_dact, void* dgu, long long ld_dgu,
-                     long long R, int I, gamer_stream_t stream);
+                     long long R, int I, const int* row_ids, const gamer_dropout_t* drop, gamer_stream_t stream);
+/* out = x + dropout(y * silu(g))   (cross attention: o_proj(a) * silu(gating(h)), Qwen3Multi/model.py:146-147,235) */
 int gamer_gate_residual_fwd(const void* x, const void* y, const void* g, long long ld_g, void* out, long long R, int W,
-                            gamer_stream_t stream);
+                            const gamer_dropout_t* drop, gamer_stream_t stream);
 int gamer_gate_residual_bwd(const void* dout, const void* y, const void* g, long long ld_g, void* dy, void* dg,
-                            long long ld_dg, long long R, int W, gamer_stream_t stream);
+                            long long ld_dg, long long R, int W, const gamer_dropout_t* drop, gamer_stream_t stream);
+/* dst[r] = dropout_mask[rows[r]] * src[rows[r]]  (0 where rows[r] < 0) */
 int gamer_gather_rows(const void* src, long long ld_src, const int* rows, const int* n_rows_dev, long long n_rows_max,
-                      void* dst, long long ld_dst, int W, gamer_stream_t stream);
+                      void* dst, long long ld_dst, int W, const gamer_dropout_t* drop, gamer_stream_t stream);
+/* out = dropout(in) with the mask of `drop` (backward of a residual-branch dropout fused into a GEMM epilogue) */
+int gamer_dropout_apply(const void* in, void* out, long long R, int W, const gamer_dropout_t* drop,
+                        gamer_stream_t stream);
 
 /* ---- K8: fused softmax cross-entropy (ForCausalLMLoss, Qwen3Multi/model.py:904-922) ---------------------------- */
 int gamer_ce_fwd_bwd(const float* logits, long long ld_l, const long long* labels, long long R, int V, int ignore_index,

@@ -148,22 +148,27 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return x * cos.unsqueeze(1) + rot * sin.unsqueeze(1)
 
 
-def masked_attention(q, k, v, allow, scale):
+def masked_attention(q, k, v, allow, scale, zp=None):
     """q [B,Hq,S,d], k/v [B,Hkv,T,d], allow bool [B,S,T].  Additive finfo(fp32).min mask then softmax, exactly
-    what SDPA computes for the reference: a row with no allowed key is *uniform over all T keys* (quirk Q1)."""
+    what SDPA computes for the reference: a row with no allowed key is *uniform over all T keys* (quirk Q1).
+    `zp` [B,Hq,S,T] (training): multiplicative dropout mask on the probabilities (SDPA dropout_p,
+    Qwen3Multi/model.py:139).  Documented deviation of the CUDA path, restated here: uniform rows are not dropped
+    (they keep their expectation, the mean of V)."""
     g = q.shape[1] // k.shape[1]
     k = k.repeat_interleave(g, dim=1)
     v = v.repeat_interleave(g, dim=1)
     bias = torch.where(allow, 0.0, torch.finfo(torch.float32).min).unsqueeze(1)
     s = torch.matmul(q, k.transpose(-1, -2)) * scale + bias
     p = torch.softmax(s, dim=-1)
+    if zp is not None:
+        p = torch.where(allow.any(-1).view(allow.shape[0], 1, -1, 1), p * zp, p)
     return torch.matmul(p, v)
 
 
 # --------------------------------------------------------------------------------------------------------------
 # A6 attention block, A7 routed FFN, A8 layer
 # --------------------------------------------------------------------------------------------------------------
-def attention_block(spec, W, pre, h, cos, sin, allow, action_index, is_cross, cache=None):
+def attention_block(spec, W, pre, h, cos, sin, allow, action_index, is_cross, cache=None, zp=None):
     """Qwen3MultiAttention.forward (Qwen3Multi/model.py:75-150); with is_cross=False and no behaviour terms it is
     also the third-party Qwen3MoeAttention used by Qwen3SessionMoe.  `cache` = dict(k=,v=) of earlier keys."""
     B, S, _ = h.shape
@@ -185,7 +190,7 @@ def attention_block(spec, W, pre, h, cos, sin, allow, action_index, is_cross, ca
             k = torch.cat([cache["k"], k], dim=2)
             v = torch.cat([cache["v"], v], dim=2)
         cache["k"], cache["v"] = k, v
-    a = masked_attention(q, k, v, allow, d ** -0.5)
+    a = masked_attention(q, k, v, allow, d ** -0.5, zp)
     a = a.transpose(1, 2).reshape(B, S, spec.n_q * d)
     out = F.linear(a, W[pre + "o_proj.weight"])
     if is_cross:
@@ -193,31 +198,47 @@ def attention_block(spec, W, pre, h, cos, sin, allow, action_index, is_cross, ca
     return out
 
 
-def routed_ffn(spec, W, pre, h, position_index, behavior_index, inject, sparse):
+def routed_ffn(spec, W, pre, h, position_index, behavior_index, inject, sparse, zi=None):
     """MyQwen3SparseMLP.forward (Qwen3Moe/FFN.py:53-72): expert = position_index (hard routing);
-    expert(x) = down(silu(gate x) * up x) (FFN.py:25-27)."""
+    expert(x) = down(dropout(silu(gate x) * up x)) (FFN.py:25-27); `zi` [B,S,I] = that dropout's mask (training)."""
     x = h
     if inject:
         x = torch.cat([x, F.embedding(behavior_index, W[pre + "behavior_embedding.weight"])], dim=-1)
 
-    def expert(p, t):
-        return F.linear(F.silu(F.linear(t, W[p + "gate_proj.weight"])) * F.linear(t, W[p + "up_proj.weight"]),
-                        W[p + "down_proj.weight"])
+    def expert(p, t, z):
+        a = F.silu(F.linear(t, W[p + "gate_proj.weight"])) * F.linear(t, W[p + "up_proj.weight"])
+        if z is not None:
+            a = a * z
+        return F.linear(a, W[p + "down_proj.weight"])
 
     if not sparse:
-        return expert(pre + "mlp.", x)
+        return expert(pre + "mlp.", x, zi)
     out = torch.zeros_like(h)
     for e in range(spec.n_experts):
         sel = position_index == e
         if sel.any():
-            out[sel] = expert(f"{pre}experts.expert_{e}.", x[sel])
+            out[sel] = expert(f"{pre}experts.expert_{e}.", x[sel], None if zi is None else zi[sel])
     return out
 
 
 def backbone(spec: Spec, W: dict, ids, am, positions, rope_pos, self_allow, cross_allow, context_ids=None,
-             caches=None):
+             caches=None, drop=None):
     """Embedding -> router -> layers -> final norm.  (Qwen3MultiModel.forward, Qwen3Multi/model.py:744-880;
-    Qwen3SessionMoeModel.forward, Qwen3SessionMoe/model.py:471-587.)"""
+    Qwen3SessionMoeModel.forward, Qwen3SessionMoe/model.py:471-587.)  `drop` (oracle/dropout_masks.OracleDropout):
+    training-mode dropout masks — nn.Dropout on each residual branch (Qwen3Multi/model.py:217,235,241), inside the
+    experts (Qwen3Moe/FFN.py:26) and on the attention probabilities (:139)."""
+    from oracle import dropout_masks as dm
+    B, S = ids.shape
+
+    def zh(l, kind, width):
+        return None if drop is None else drop.hidden(l, kind, B, S, width)
+
+    def zp(l, kind):
+        return None if drop is None else drop.attn(l, kind, B, spec.n_q, S)
+
+    def dropped(branch, z):
+        return branch if z is None else branch * z
+
     x = F.embedding(ids, W["model.embed_tokens.weight"], padding_idx=spec.pad)   # padding_idx=4: Q10 (model.py:263)
     pos_idx, beh_idx, act_idx = route(spec, ids, positions, context_ids)
     cos, sin = rope_cos_sin(spec, rope_pos)
@@ -225,17 +246,20 @@ def backbone(spec: Spec, W: dict, ids, am, positions, rope_pos, self_allow, cros
         p = f"model.layers.{l}."
         c = caches[l] if caches is not None else None
         h = rmsnorm(x, W[p + "input_layernorm.weight"], spec.eps)
-        x = x + attention_block(spec, W, p + "self_attn.", h, cos, sin, self_allow, None, False,
-                                None if c is None else c["self"])
+        x = x + dropped(attention_block(spec, W, p + "self_attn.", h, cos, sin, self_allow, None, False,
+                                        None if c is None else c["self"], zp(l, dm.SITE_SELF_P)),
+                        zh(l, dm.SITE_SELF_OUT, spec.hidden))
         if l in spec.cross_layers:
             h = rmsnorm(x, W[p + "post_self_attention_layernorm.weight"], spec.eps)
-            x = x + attention_block(spec, W, p + "cross_attn.", h, cos, sin, cross_allow, act_idx, True,
-                                    None if c is None else c["cross"])
+            x = x + dropped(attention_block(spec, W, p + "cross_attn.", h, cos, sin, cross_allow, act_idx, True,
+                                            None if c is None else c["cross"], zp(l, dm.SITE_CROSS_P)),
+                            zh(l, dm.SITE_CROSS_OUT, spec.hidden))
         post = "post_attention_layernorm.weight" if spec.variant == "Qwen3SessionMoe" else \
             "post_cross_attention_layernorm.weight"
         h = rmsnorm(x, W[p + post], spec.eps)
-        x = x + routed_ffn(spec, W, p + "mlp.", h, pos_idx, beh_idx, l in spec.inject_layers,
-                           l in spec.sparse_layers)
+        x = x + dropped(routed_ffn(spec, W, p + "mlp.", h, pos_idx, beh_idx, l in spec.inject_layers,
+                                   l in spec.sparse_layers, zh(l, dm.SITE_FFN_INNER, spec.inter)),
+                        zh(l, dm.SITE_FFN_OUT, spec.hidden))
     return rmsnorm(x, W["model.norm.weight"], spec.eps), (pos_idx, beh_idx, act_idx)
 
 
@@ -250,7 +274,7 @@ def mask_kinds(spec: Spec):
 
 
 def forward(spec: Spec, W: dict, input_ids, attention_mask, labels=None, session_ids=None,
-            extended_session_ids=None, actions=None, num_items_in_batch=None, return_hidden=False):
+            extended_session_ids=None, actions=None, num_items_in_batch=None, return_hidden=False, drop=None):
     """Full (uncached) forward = Qwen3MultiWithTemperature.forward (Qwen3Multi/model.py:928-1013) /
     Qwen3SessionMoeWithTemperature.forward (Qwen3SessionMoe/model.py:633-735).
 
@@ -268,7 +292,8 @@ def forward(spec: Spec, W: dict, input_ids, attention_mask, labels=None, session
         rope_pos = extended_session_ids                                   # Qwen3SessionMoe/model.py:688-703
     else:
         rope_pos = positions.unsqueeze(0)                                  # Qwen3Multi/model.py:787-794
-    hidden, routes = backbone(spec, W, input_ids, attention_mask, positions, rope_pos, self_allow, cross_allow)
+    hidden, routes = backbone(spec, W, input_ids, attention_mask, positions, rope_pos, self_allow, cross_allow,
+                              drop=drop)
     logits = F.linear(hidden, W["lm_head.weight"])
     out = {"hidden": hidden, "route": routes, "loss": None}
     if labels is not None:
