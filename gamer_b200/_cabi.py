@@ -99,9 +99,10 @@ LAUNCHES = {"gamer_route_perm_build": 3, "gamer_embed_sort_build": 3, "gamer_att
 class Profile:
     """Optional per-entry-point device timing (CUDA events on the launching stream) + algorithmic work counters."""
 
-    def __init__(self):
+    def __init__(self, only=None):
         self.records = {}      # name -> list of (start_event, end_event, flops, bytes)
         self.launches = 0
+        self.only = only       # set of entry points to time (None = all); the others are only counted
 
     def summary(self):
         out = {}
@@ -127,7 +128,7 @@ def call(name: str, *args, work=(0, 0)):
         return
     import torch
     prof.launches += LAUNCHES.get(name, 1)
-    if prof.records is None:                      # count-only mode
+    if prof.records is None or (prof.only is not None and name not in prof.only):      # count-only
         check(fn(*args), name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -658,6 +658,7 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (kind_uses_sess<KIND>()) sess_i = p.sess[(long long)b * p.L + i];
         }
         const int istart = (i / p.P) * p.P;
+        const DropParams drop = drop_resolve(p.drop);
         unsigned allvalid = 0;  // bit t: every key of 128-key tile t is valid (CAUSAL tiles off the diagonal need no mask)
         if (KIND == MASK_CAUSAL) {
             for (int t = 0; t < p.k_tiles; ++t) allvalid |= (p.tflag[b * p.k_tiles + t] != 0 ? 1u : 0u) << t;
@@ -704,7 +705,7 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if constexpr (DROP) {
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
-                    const uint4 rnd = drop_attn16(p.drop, (uint32_t)(b * p.n_q + h), (uint32_t)i, (uint32_t)(j * 4 + cb));
+                    const uint4 rnd = drop_attn16(drop, (uint32_t)(b * p.n_q + h), (uint32_t)i, (uint32_t)(j * 4 + cb));
                     const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
@@ -714,8 +715,8 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         sum[(c >> 1) & 1] += p0;
                         sum[2 + ((c >> 1) & 1)] += p1;
                         const uint32_t w = rw[e >> 2];
-                        const bool k0 = ((w >> (8 * (e & 3))) & 0xffu) >= p.drop.thresh;
-                        const bool k1 = ((w >> (8 * (e & 3) + 8)) & 0xffu) >= p.drop.thresh;
+                        const bool k0 = ((w >> (8 * (e & 3))) & 0xffu) >= drop.thresh;
+                        const bool k1 = ((w >> (8 * (e & 3) + 8)) & 0xffu) >= drop.thresh;
                         s[c >> 1] = pack_bf16(k0 ? p0 : 0.f, k1 ? p1 : 0.f);
                     }
                 }
@@ -746,7 +747,7 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(o_full, (nkt - 1) & 1);
         tc_fence_after();
         const bool uniform = !(l > 0.f);
-        const float inv = uniform ? 0.f : (DROP ? p.drop.scale : 1.f) / l;
+        const float inv = uniform ? 0.f : (DROP ? drop.scale : 1.f) / l;
         const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -1036,6 +1037,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t sP = smem_u32(smem + B_OFF_P + (wgi >> 1) * TILE_BYTES) + row * 128;
         const uint32_t sDS = smem_u32(smem + B_OFF_DS + (wgi >> 1) * TILE_BYTES) + row * 128;
         const int ch0 = (wgi & 1) * 4;
+        const DropParams drop = drop_resolve(p.drop);
         uint32_t item_n = 0, step_n = 0;
         int tn = 0;
         Trace tr = p.tr;
@@ -1091,15 +1093,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 if constexpr (DROP) {
                     if (!uni) {
                         keep = 0u;
-                        zs = p.drop.scale;
+                        zs = drop.scale;
 #pragma unroll
                         for (int cb = 0; cb < 2; ++cb) {
-                            const uint4 rnd = drop_attn16(p.drop, (uint32_t)(b * p.n_q + 2 * g + hh), (uint32_t)i,
+                            const uint4 rnd = drop_attn16(drop, (uint32_t)(b * p.n_q + 2 * g + hh), (uint32_t)i,
                                                           (uint32_t)((jbase >> 4) + cb));
                             const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                             for (int e = 0; e < 16; ++e)
-                                keep |= ((((rw[e >> 2] >> (8 * (e & 3))) & 0xffu) >= p.drop.thresh) ? 1u : 0u) << (cb * 16 + e);
+                                keep |= ((((rw[e >> 2] >> (8 * (e & 3))) & 0xffu) >= drop.thresh) ? 1u : 0u) << (cb * 16 + e);
                         }
                     }
                 }

@@ -98,10 +98,11 @@ struct DropParams {
     uint32_t site;     // which dropout call of the step (layer * 8 + kind)
     uint32_t thresh;   // drop when the element's random value < thresh (0 = dropout off)
     float scale;       // 1 / keep probability
+    const uint32_t* off_dev;  // optional device word XOR-ed into k1 when the kernel starts (CUDA-graph replays)
 };
 
 static inline DropParams make_drop(const gamer_dropout_t* d, int bits) {
-    DropParams r{0u, 0u, 0u, 0u, 1.0f};
+    DropParams r{0u, 0u, 0u, 0u, 1.0f, nullptr};
     if (d == nullptr || !(d->p > 0.0f)) return r;
     const uint32_t full = 1u << bits;
     uint32_t t = (uint32_t)((double)d->p * (double)full);
@@ -111,7 +112,15 @@ static inline DropParams make_drop(const gamer_dropout_t* d, int bits) {
     r.site = d->site;
     r.thresh = t;
     r.scale = (float)((double)full / (double)(full - t));
+    r.off_dev = d->offset_dev;
     return r;
+}
+
+// kernels call this once: folds the device-side offset word into the key
+__device__ __forceinline__ DropParams drop_resolve(DropParams d) {
+    if (d.thresh != 0u && d.off_dev != nullptr) d.k1 ^= __ldg(d.off_dev);
+    d.off_dev = nullptr;
+    return d;
 }
 
 __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

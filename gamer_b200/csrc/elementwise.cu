@@ -13,6 +13,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, bf16* __restrict__ act, long long ld_act,
                                   long long R, int I, const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
+    dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row;
@@ -34,6 +35,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
                                   long long ld_dact, bf16* __restrict__ dgu, long long ld_dgu, long long R, int I,
                                   const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
+    dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row;
@@ -62,6 +64,7 @@ __global__ void gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16*
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ out, long long R,
                                          int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row;
@@ -84,6 +87,7 @@ __global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ dy,
                                          bf16* __restrict__ dg, long long ld_dg, long long R, int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row;
@@ -109,6 +113,7 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long ld_sr
                                    const int* __restrict__ n_rows_dev, long long n_rows_max, bf16* __restrict__ dst,
                                    long long ld_dst, int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    dp = drop_resolve(dp);
     const long long n_rows = n_rows_dev ? min((long long)*n_rows_dev, n_rows_max) : n_rows_max;
     const long long total = n_rows * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

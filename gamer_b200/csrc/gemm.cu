@@ -200,6 +200,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int trow = quarter * 32 + lane;
+        const DropParams drop = drop_resolve(p.drop);
         int acc = 0;
         uint32_t acc_phase = 0, tcount = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
@@ -235,8 +236,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float v[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]) * p.alpha;
-                            if (p.drop.thresh)
-                                drop_apply8(p.drop, (uint32_t)(row0 + trow), (uint32_t)((n_blk * BLOCK_N + c * 32 + q * 8) >> 3), v);
+                            if (drop.thresh)
+                                drop_apply8(drop, (uint32_t)(row0 + trow), (uint32_t)((n_blk * BLOCK_N + c * 32 + q * 8) >> 3), v);
                             if (has_resid) {
                                 bf16x8 rv;
                                 lds128(addr, rv.u[0], rv.u[1], rv.u[2], rv.u[3]);
@@ -285,9 +286,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-                        if (p.drop.thresh) {
+                        if (drop.thresh) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) drop_apply8(p.drop, (uint32_t)orow, (uint32_t)((col0 >> 3) + q), v + 8 * q);
+                            for (int q = 0; q < 4; ++q) drop_apply8(drop, (uint32_t)orow, (uint32_t)((col0 >> 3) + q), v + 8 * q);
                         }
                         const bool full = (col0 + 32 <= p.N);
                         if (p.resid != nullptr) {

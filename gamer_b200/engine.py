@@ -207,6 +207,20 @@ class FlatPack(Pack):
                 d["beh_emb"] = Wb[p + "beh_emb"]
             self.layers.append(d)
 
+    def refresh(self):
+        """Re-derive the transposed (dgrad) copies IN PLACE after the optimizer rewrote the flat bf16 buffer: every
+        operand keeps its address, so CUDA graphs captured over this pack stay valid."""
+        self.emb_t[:, :self.emb.shape[0]].copy_(self.emb.t())
+        for d in self.layers:
+            d["w_qkv_t"].copy_(d["w_qkv"].t())
+            d["w_o_t"].copy_(d["w_o"].t())
+            if "c_w_qkvg" in d:
+                d["c_w_qkvg_t"].copy_(d["c_w_qkvg"].t())
+                d["c_w_o_t"].copy_(d["c_w_o"].t())
+            E_ = d["w_gu_t"].shape[0] // d["w_gu"].shape[1]
+            d["w_gu_t"].view(E_, d["w_gu"].shape[1], -1).copy_(d["w_gu"].view(E_, -1, d["w_gu"].shape[1]).transpose(1, 2))
+            d["w_d_t"].view(E_, d["w_d"].shape[1], -1).copy_(d["w_d"].view(E_, -1, d["w_d"].shape[1]).transpose(1, 2))
+
 
 def rope_tables(arch: Arch, n_pos: int, device):
     """cos/sin [n_pos, head_dim/2] fp32, computed as Qwen3RotaryEmbedding does (fp32 outer product, then cos/sin)."""
@@ -237,12 +251,14 @@ class DropCtx:
     offset: int
     p_hidden: float
     p_attn: float
+    offset_dev: torch.Tensor | None = None     # device int32[1] XOR-ed into the key at run time (CUDA-graph replays)
 
     def site(self, layer: int, kind: int):
         p = self.p_attn if kind in (SITE_SELF_P, SITE_CROSS_P) else self.p_hidden
         if p <= 0.0:
             return None
-        return K.Dropout(self.seed & 0xFFFFFFFFFFFFFFFF, self.offset & 0xFFFFFFFF, layer * 8 + kind, float(p))
+        return K.Dropout(self.seed & 0xFFFFFFFFFFFFFFFF, self.offset & 0xFFFFFFFF, layer * 8 + kind, float(p),
+                         None if self.offset_dev is None else self.offset_dev.data_ptr())
 
 
 def _site(drop, layer, kind):

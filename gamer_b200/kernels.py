@@ -20,7 +20,8 @@ def _stream():
 class Dropout(ctypes.Structure):
     """gamer_dropout_t (include/gamer_b200.h): one dropout call site of a forward pass; the backward passes the same
     struct and the kernels regenerate the Philox mask."""
-    _fields_ = [("seed", ctypes.c_ulonglong), ("offset", ctypes.c_uint), ("site", ctypes.c_uint), ("p", ctypes.c_float)]
+    _fields_ = [("seed", ctypes.c_ulonglong), ("offset", ctypes.c_uint), ("site", ctypes.c_uint), ("p", ctypes.c_float),
+                ("offset_dev", ctypes.c_void_p)]
 
 
 def _drop(d):

@@ -174,7 +174,12 @@ class _GamerCausalLM(PreTrainedModel):
         self._drop_seed = int(seed)
         self._drop_calls = 0
 
-    def _next_drop(self):
+    def _drop_config(self):
+        """(seed, p_hidden, p_attn) of the training-mode dropout, or None when the model is in eval mode / p = 0."""
+        d = self._next_drop(advance=False)
+        return None if d is None else (d.seed, d.p_hidden, d.p_attn)
+
+    def _next_drop(self, advance=True):
         """Dropout context of the next training-mode forward (nn.Dropout(config.dropout_rate) / SDPA
         dropout_p=config.attention_dropout in the reference, Qwen3Multi/model.py:139,177); None in eval mode."""
         p_h = float(getattr(self.config, "dropout_rate", 0.0) or 0.0)
@@ -185,7 +190,8 @@ class _GamerCausalLM(PreTrainedModel):
             rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
             self._drop_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03 * (rank + 1)) & (2 ** 64 - 1)
         d = E.DropCtx(self._drop_seed, self._drop_calls, p_h, p_a)
-        self._drop_calls += 1
+        if advance:
+            self._drop_calls += 1
         return d
 
     def _get_pack(self, arch):

@@ -10,7 +10,11 @@ loop underneath it, restated B200-first:
   * gradients are accumulated by the wgrad kernels straight into a flat fp32 buffer of the same layout; one layer = one
     contiguous range = one NCCL all-reduce bucket, launched (async, NCCL's stream) as soon as that layer's backward
     kernels are enqueued, so the reduction of layer l overlaps the backward of layers l-1..0;
-  * one fused AdamW kernel updates p/m/v and emits the bf16 operand copy for the next step's GEMMs.
+  * one fused AdamW kernel updates p/m/v and emits the bf16 operand copy for the next step's GEMMs;
+  * the forward + backward of a micro-batch (~1500 kernel launches, ~11 us of Python/ctypes each) is captured ONCE per
+    batch shape into a CUDA graph and replayed: inputs are copied into static buffers, every operand (flat weights,
+    transposed copies, gradient buffer) keeps its address, and the dropout masks change per replay through a device-side
+    offset word.  With graphs the gradient all-reduce is launched after the last micro-batch's replay.
 """
 from __future__ import annotations
 
@@ -29,8 +33,11 @@ def _stream():
 
 
 class NativeTrainer:
+    BATCH_KEYS = ("input_ids", "attention_mask", "labels", "actions", "session_ids", "extended_session_ids")
+
     def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
-                 warmup_steps=0, total_steps=None, process_group=None, min_lr_ratio=0.0):
+                 warmup_steps=0, total_steps=None, process_group=None, min_lr_ratio=0.0, use_cuda_graphs=True,
+                 max_graphs=4):
         self.model = model
         self.arch = model.arch
         dev = next(model.parameters()).device
@@ -73,6 +80,12 @@ class NativeTrainer:
         self.lut = E.behaviour_lut(a, dev)
         call("gamer_cast_f32_bf16", ptr(self.flat_p), ptr(self.flat_bf16), n, _stream())
         self.pack = E.FlatPack(a, self.flat_bf16, self.flat_p)
+        self.use_cuda_graphs = use_cuda_graphs
+        self.max_graphs = max_graphs
+        self.graphs = {}                   # shape key -> captured micro-batch (fwd + bwd)
+        self.seen = {}                     # shape key -> eager runs so far (capture on the second occurrence)
+        self.drop_off = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side dropout offset, +1 per micro-batch
+        self.micro_batches = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def current_lr(self):
@@ -93,17 +106,67 @@ class NativeTrainer:
         self.reducer.launch("model.norm.weight" if layer_idx == a.n_layers else
                             ("model.embed_tokens.weight" if layer_idx < 0 else f"L{layer_idx}"))
 
-    def forward_backward(self, batch, inv_norm, last_micro=True):
+    def _drop_ctx(self):
+        cfg = self.model._drop_config()
+        if cfg is None:
+            return None
+        seed, p_h, p_a = cfg
+        return E.DropCtx(seed, 0, p_h, p_a, offset_dev=self.drop_off)
+
+    def _run_micro(self, batch, inv_norm, hook):
         a = self.arch
         ids = batch["input_ids"].contiguous()
         meta = E.make_meta(a, ids, batch.get("attention_mask"), batch.get("actions"), batch.get("session_ids"),
                            batch.get("extended_session_ids"))
         shifted = E.shift_labels(batch["labels"])
         loss, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature),
-                                  drop=self.model._next_drop())
+                                  drop=self._drop_ctx())
         one = torch.ones((), dtype=torch.float32, device=self.dev)
-        E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=self._bucket_hook if last_micro else None)
+        E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=hook)
         return loss
+
+    def _graph_key(self, batch):
+        cfg = self.model._drop_config()
+        return (tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self.BATCH_KEYS if batch.get(k) is not None),
+                cfg[1:] if cfg else None, float(self.model.temperature))
+
+    def _capture(self, key, batch, inv_norm):
+        """Capture forward + backward of one micro-batch shape.  The eager run that precedes every capture (see
+        forward_backward) has already initialised the lazily configured kernels."""
+        static = {k: torch.empty_like(batch[k]) for k in self.BATCH_KEYS if batch.get(k) is not None}
+        for k, v in static.items():
+            v.copy_(batch[k])
+        s_inv = inv_norm.clone()
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            loss = self._run_micro(static, s_inv, None)
+        if len(self.graphs) >= self.max_graphs:
+            self.graphs.pop(next(iter(self.graphs)))
+        self.graphs[key] = (g, static, s_inv, loss)
+        return self.graphs[key]
+
+    def forward_backward(self, batch, inv_norm, last_micro=True):
+        """Forward + backward of one micro-batch into the flat gradient buffer; returns its loss (device scalar)."""
+        self.drop_off.add_(1)
+        self.micro_batches += 1
+        if not self.use_cuda_graphs:
+            return self._run_micro(batch, inv_norm, self._bucket_hook if last_micro else None)
+        key = self._graph_key(batch)
+        entry = self.graphs.get(key)
+        if entry is None:
+            self.seen[key] = self.seen.get(key, 0) + 1
+            if self.seen[key] < 2:                 # first occurrence of a shape: eager (also the kernels' warm-up)
+                return self._run_micro(batch, inv_norm, self._bucket_hook if last_micro else None)
+            entry = self._capture(key, batch, inv_norm)      # capture records, it does not execute
+        g, static, s_inv, loss = entry
+        for k, v in static.items():
+            v.copy_(batch[k], non_blocking=True)
+        s_inv.copy_(inv_norm)
+        g.replay()
+        if last_micro:
+            self.reducer.launch_all_reverse()
+        return loss.clone()
 
     def step(self, batch, micro_batch=None):
         """One optimizer step over `batch` (device tensors, [B, L]); `micro_batch` splits it for gradient accumulation
@@ -138,5 +201,5 @@ class NativeTrainer:
         call("gamer_adamw_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v),
              ptr(self.decay_mask), ptr(self.flat_bf16), n, ptr(self.hp), self.betas[0], self.betas[1], self.eps,
              self.wd, ptr(gn), float(self.max_grad_norm or 0.0), 1.0 / self.world, _stream())
-        self.pack = E.FlatPack(self.arch, self.flat_bf16, self.flat_p)
+        self.pack.refresh()                        # in place: operands keep their addresses (captured graphs stay valid)
         self.model._pack = None                    # the kernel wrote the weights behind autograd's back

@@ -45,6 +45,8 @@ typedef struct {
     unsigned int site;       /* dropout call within the pass: layer * 8 + {0 self P, 1 self out, 2 cross P, 3 cross out,
                                 4 expert inner, 5 FFN out} */
     float p;
+    const unsigned int* offset_dev; /* optional DEVICE word XOR-ed into the key at kernel run time: lets a captured CUDA
+                                       graph draw fresh masks on every replay (NULL = none) */
 } gamer_dropout_t;
 
 /* ---- K1: embedding gather + router indices ------------------------------------------------------------------

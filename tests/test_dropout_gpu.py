@@ -198,4 +198,4 @@ def test_trainer_steps_with_dropout():
     losses = [tr.step(batch, micro_batch=8).item() for _ in range(8)]
     assert all(l == l and abs(l) < 1e4 for l in losses), losses
     assert losses[-1] < losses[0], losses
-    assert m._drop_calls == 16
+    assert tr.micro_batches == 16

@@ -57,3 +57,30 @@ def test_native_step_matches_oracle_adamw():
     # a second step runs on the refreshed pack and lowers the loss on the same batch
     loss2 = tr.step(batch, micro_batch=6)
     assert loss2.item() < loss.item()
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured micro-batch graph (trainer default) reproduces the eager launch sequence: same losses over several
+    optimizer steps with dropout ON (the device-side offset word gives every replay the masks the eager path draws),
+    and the graph really is replayed."""
+    from gamer_b200.trainer import NativeTrainer
+    g = load_golden("train_qwen3multi.pt")
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    losses = {}
+    for mode in (False, True):
+        m = build_model(g).train()
+        m.config.dropout_rate = 0.2
+        m.config.attention_dropout = 0.2
+        m.set_dropout_seed(1234)
+        tr = NativeTrainer(m, lr=1e-3, max_grad_norm=1.0, use_cuda_graphs=mode)
+        losses[mode] = [tr.step(batch, micro_batch=3).item() for _ in range(5)]   # 6 rows -> 2 micro-batches of 3
+        if mode:
+            assert len(tr.graphs) == 1 and tr.micro_batches == 10
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (losses[False], losses[True])
+    assert losses[True][-1] < losses[True][0]
+    # without dropout the replayed loss of the first step equals the golden loss
+    m = build_model(g).train()
+    tr = NativeTrainer(m, lr=1e-3, use_cuda_graphs=True)
+    l0 = tr.step(batch, micro_batch=2).item()                                      # 3 micro-batches: eager, capture, replay
+    assert abs(l0 - g["loss"].item()) <= 5e-3 * max(1.0, abs(g["loss"].item())), (l0, g["loss"].item())
