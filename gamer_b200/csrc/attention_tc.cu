@@ -815,11 +815,14 @@ struct BwdParams {
 
 template <int KIND>
 __device__ __forceinline__ void bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask) {
-    const int per = p.B * p.n_kv;
-    kt = w / per;  // key tile 0 meets the most query tiles: heaviest first
-    const int rem = w % per;
-    b = rem / p.n_kv;
-    g = rem % p.n_kv;
+    // (sequence, kv head)-major: the k_tiles items of one group run at the same time on neighbouring CTAs, so their Q / dO
+    // tiles and dQ accumulator tiles are shared through L2 instead of being re-fetched from HBM once per key tile.  The key
+    // tile is rotated by the group index: with a grid stride that is a multiple of k_tiles a CTA would otherwise always draw
+    // the same (heaviest or lightest) key tile.
+    const int grp = w / p.k_tiles;
+    kt = (w % p.k_tiles + grp) % p.k_tiles;
+    b = grp / p.n_kv;
+    g = grp % p.n_kv;
     const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
     if (kind_causal<KIND>()) qmask = ((all >> kt) << kt) | (p.uni_bits[b] & all);
     else qmask = all;
@@ -883,11 +886,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* pds_full = bars + 11;
     uint64_t* p_free = bars + 12;
     uint64_t* ds_free = bars + 13;
-    uint64_t* dq_full = bars + 14;
-    uint64_t* dq_free = bars + 15;
-    uint64_t* dkv_full = bars + 16;
-    uint64_t* dkv_free = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* dq_full = bars + 14;   // [2]: dQ lives in two TMEM buffers, so dQ(n) does not wait for the drain of dQ(n-1)
+    uint64_t* dq_free = bars + 16;   // [2]
+    uint64_t* dkv_full = bars + 18;
+    uint64_t* dkv_free = bars + 19;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -909,8 +912,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(pds_full, 512);
         mbar_init(p_free, 1);
         mbar_init(ds_free, 1);
-        mbar_init(dq_full, 1);
-        mbar_init(dq_free, 128);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&dq_full[s], 1);
+            mbar_init(&dq_free[s], 128);
+        }
         mbar_init(dkv_full, 1);
         mbar_init(dkv_free, 128);
         fence_barrier_init();
@@ -920,7 +925,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+    // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448) and [448,512)
     constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
 
     if (warp == 0) {
@@ -1008,13 +1013,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0);   // dV += P^T dO
                     umma_commit(p_free);
                     issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0);               // dK += dS^T Q
-                    if (step_n > 0) {
-                        mbar_wait(dq_free, (step_n - 1) & 1);
+                    const uint32_t db = step_n & 1, du = step_n >> 1;
+                    if (du > 0) {
+                        mbar_wait(&dq_free[db], (du - 1) & 1);
                         tc_fence_after();
                     }
                     trace_pt(p.tr, 0, tn, 5);
-                    issue_nn_128x64x128(tmem_base + T_DQ, sds, sk, false);               // dQ = dS K
-                    umma_commit(dq_full);
+                    issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false);     // dQ = dS K
+                    umma_commit(&dq_full[db]);
                     umma_commit(ds_free);
                     umma_commit(&qdo_free[st]);
                     if (n + 1 == N) {
@@ -1179,18 +1185,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 int hh, qt;
                 bwd_step(qmask, nph, n, hh, qt);
                 trace_pt(tr, 2, tn, 40);
-                mbar_wait(dq_full, step_n & 1);
+                const uint32_t db = step_n & 1, du = step_n >> 1;
+                mbar_wait(&dq_full[db], du & 1);
                 tc_fence_after();
                 trace_pt(tr, 2, tn, 41);
                 float* dst = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     uint32_t o[32];
-                    tmem_ld_32x32(t_dq + half * 32, o);
+                    tmem_ld_32x32(t_dq + db * 64 + half * 32, o);
                     tmem_ld_wait();
                     if (half == 1) {
                         tc_fence_before();
-                        mbar_arrive(dq_free);
+                        mbar_arrive(&dq_free[db]);
                     }
                     if (row == 0) bulk_wait_read0();  // the previous bulk op has finished reading the staging buffer
                     trace_pt(tr, 2, tn, 42 + half);
