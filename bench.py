@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--max-his-len", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from the host (A/B switch)")
+    ap.add_argument("--no-eval", action="store_true", help="skip the secondary constrained-beam-search evaluation leg")
+    ap.add_argument("--eval-users", type=int, default=256)
     ap.add_argument("--cpu-sample", type=int, default=8, help="rows of the bounded CPU-baseline sample")
     return ap.parse_args()
 
@@ -121,6 +123,73 @@ def cpu_reference_step_fn(max_his_len, rows, seed=0):
         return float(out["loss"].detach())
 
     return step, rows
+
+
+def eval_leg(args, dev, world, rank, barrier):
+    """Secondary metric of BASELINE.json (configs[2]): trie-constrained beam-search evaluation of Qwen3SessionMoe,
+    ShortVideoAD-shaped synthetic users, max_his_len=100 (prompt = 501 tokens, full length), global batch 256 users
+    sharded exactly over the ranks, 20 beams, 4 new tokens, 250k-item candidate trie.  Returns the `eval` object of the
+    JSON line: users/s with inputs resident in HBM and end to end from pinned host buffers (H2D of the prompts + D2H of the
+    decoded sequences and scores inside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    from transformers.models.qwen3_moe import Qwen3MoeConfig
+    from gamer_b200 import modeling
+    from gamer_b200 import synthetic as syn
+    from gamer_b200.distributed import shard_range
+    from gamer_b200.trie import flat_from_array, prefix_allowed_tokens_fn_by_last_token
+    cfg = Qwen3MoeConfig.from_pretrained(os.path.join(ROOT, "config", "s2s-models", "Qwen3SessionMoe"))
+    cfg.vocab_size = 1041
+    cfg.num_behavior = 3
+    cfg.behavior_maps = {"526": 0, "527": 1, "528": 2}
+    cfg.use_behavior_token = True
+    cfg.num_positions = 5
+    cfg.num_experts = 6
+    cfg.n_positions = args.max_his_len + 1
+    cfg.use_user_token = False
+    cfg.model_max_length = max(1024, 5 * (args.max_his_len + 1))
+    torch.manual_seed(43)
+    model = modeling.Qwen3SessionMoeWithTemperature(cfg).to(dev).eval()
+    cat = syn.make_catalogue(250_000, 1234)
+    items = cat.item_sequences(2)
+    fn = prefix_allowed_tokens_fn_by_last_token(flat_from_array(items), set(int(t) for t in items[:, -1]) | {syn.PAD})
+    users, beams = args.eval_users, 20
+    lo, hi = shard_range(users, rank, world)
+    batch, _ = syn.make_eval_batch(cat, users, max_his_len=args.max_his_len, target_behavior=2, seed=77, full_length=True)
+    host = {k: v[lo:hi].contiguous().pin_memory() for k, v in batch.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def decode(b):
+        return model.generate(**b, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=beams,
+                              num_return_sequences=beams, output_scores=True, return_dict_in_generate=True)
+
+    decode(resident)
+    iters = 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for name in ("value", "e2e"):
+        barrier()
+        ev0.record()
+        for _ in range(iters):
+            if name == "value":
+                o = decode(resident)
+            else:
+                o = decode({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+                seq_host, score_host = o.sequences.cpu(), o.sequences_scores.cpu()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = users * iters / (float(t.item()) / 1e3)
+    n = hi - lo
+    return {"metric": "eval_users_per_s", "value": out["value"], "unit": "users/s",
+            "config": {"workload": f"Qwen3SessionMoe trie-constrained beam search (configs[2]), max_his_len={args.max_his_len}, "
+                                   f"prompt 501 tokens, {users} users per batch, {beams} beams, 4 new tokens, "
+                                   f"250k-item trie", "users_per_gpu": n, "iters": iters},
+            "e2e": {"value": out["e2e"], "unit": "users/s",
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * world,
+                    "d2h_bytes_per_step": int(seq_host.numel() * 8 + score_host.numel() * 4) * world}}
 
 
 def run_reference(args):
@@ -262,6 +331,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = args.global_batch * args.steps / (float(t.item()) / 1e3)
 
+    eval_obj = None
+    graphs_flag = bool(trainer.use_cuda_graphs)
+    if not args.no_eval:
+        del trainer, resident
+        torch.cuda.empty_cache()
+        eval_obj = eval_leg(args, dev, world, rank, barrier)
+
     if rank == 0:
         peaks = {}
         try:
@@ -307,10 +383,12 @@ def main():
                                       f"Philox masks regenerated in the backward)",
                            "l2_policy": "inputs and activations (>1 GB per micro-batch) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks.summary(), "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
-                "cuda_graphs": bool(trainer.use_cuda_graphs),
+                "cuda_graphs": graphs_flag,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 4 * world, "last_loss": loss_host},
                 "roofline": roof, "kernel_breakdown": breakdown}
+        if eval_obj is not None:
+            line["eval"] = eval_obj
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

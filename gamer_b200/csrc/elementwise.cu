@@ -9,15 +9,30 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// flat vector index -> (row, first column): a shift and a mask when the row holds a power-of-two number of 16-byte
+// vectors (every shipped width), instead of a 64-bit division per element
+__device__ __forceinline__ int pow2_shift(int n) { return (n & (n - 1)) == 0 ? 31 - __clz(n) : -1; }
+__device__ __forceinline__ void split_index(long long i, int vec_per_row, int vshift, long long& r, int& c) {
+    if (vshift >= 0) {
+        r = i >> vshift;
+        c = (int)(i & (vec_per_row - 1)) * 8;
+    } else {
+        r = i / vec_per_row;
+        c = (int)(i % vec_per_row) * 8;
+    }
+}
+
 // gu: [R, 2*I] (gate | up), act: [R, I] = dropout(silu(gate) * up); the mask row is row_ids[r] (token row) when given
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, bf16* __restrict__ act, long long ld_act,
                                   long long R, int I, const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
+    const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = (int)(i % vec_per_row) * 8;
+        long long r;
+        int c;
+        split_index(i, vec_per_row, vshift, r, c);
         float g[8], u[8], o[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
@@ -35,11 +50,13 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
                                   long long ld_dact, bf16* __restrict__ dgu, long long ld_dgu, long long R, int I,
                                   const int* __restrict__ row_ids, DropParams dp) {
     const int vec_per_row = I / 8;
+    const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = (int)(i % vec_per_row) * 8;
+        long long r;
+        int c;
+        split_index(i, vec_per_row, vshift, r, c);
         float g[8], u[8], d[8], dg[8], du[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
@@ -64,11 +81,13 @@ __global__ void gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16*
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ out, long long R,
                                          int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = (int)(i % vec_per_row) * 8;
+        long long r;
+        int c;
+        split_index(i, vec_per_row, vshift, r, c);
         float xf[8], yf[8], gf[8], o[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + r * W + c), xf);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
@@ -87,11 +106,13 @@ __global__ void gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf
                                          const bf16* __restrict__ g, long long ld_g, bf16* __restrict__ dy,
                                          bf16* __restrict__ dg, long long ld_dg, long long R, int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = (int)(i % vec_per_row) * 8;
+        long long r;
+        int c;
+        split_index(i, vec_per_row, vshift, r, c);
         float d[8], yf[8], gf[8], o1[8], o2[8];
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dout + r * W + c), d);
         bf16x8_to_float(*reinterpret_cast<const bf16x8*>(y + r * W + c), yf);
@@ -113,12 +134,14 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long ld_sr
                                    const int* __restrict__ n_rows_dev, long long n_rows_max, bf16* __restrict__ dst,
                                    long long ld_dst, int W, DropParams dp) {
     const int vec_per_row = W / 8;
+    const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long n_rows = n_rows_dev ? min((long long)*n_rows_dev, n_rows_max) : n_rows_max;
     const long long total = n_rows * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = (int)(i % vec_per_row) * 8;
+        long long r;
+        int c;
+        split_index(i, vec_per_row, vshift, r, c);
         const long long sr = rows ? (long long)rows[r] : r;
         bf16x8 v;
         v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;

@@ -40,27 +40,47 @@ __device__ __forceinline__ void route_token(const RouteArgs& a, int b, int s, lo
     beh_i = (special || (t % a.P) == 0) ? 0 : mapped;
 }
 
-__global__ void embed_route_kernel(RouteArgs a, const bf16* __restrict__ table, int H, bf16* __restrict__ x,
-                                   int* __restrict__ pos_idx, int* __restrict__ beh_idx, int* __restrict__ act_idx) {
+// A warp takes TOK consecutive tokens per iteration: lanes 0..TOK-1 load one id each (one coalesced request), run the
+// router for their token and write the three index arrays; the ids are then broadcast by shuffle and the TOK table rows
+// are copied with all their 16-byte loads in flight before the first store (the table is L2-resident: 533 KB; the
+// kernel is bound by the 512 B/token row write).
+constexpr int TOK = 8;
+
+__global__ void __launch_bounds__(256)
+embed_route_kernel(RouteArgs a, const bf16* __restrict__ table, int H, bf16* __restrict__ x,
+                   int* __restrict__ pos_idx, int* __restrict__ beh_idx, int* __restrict__ act_idx) {
     const int warps_per_block = blockDim.x >> 5;
     const long long M = (long long)a.B * a.S;
     const int lane = threadIdx.x & 31;
-    for (long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M;
-         m += (long long)gridDim.x * warps_per_block) {
-        const int b = (int)(m / a.S), s = (int)(m % a.S);
-        const long long id = a.ids[m];
-        if (lane == 0) {
+    const long long n_groups = (M + TOK - 1) / TOK;
+    for (long long grp = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); grp < n_groups;
+         grp += (long long)gridDim.x * warps_per_block) {
+        const long long m0 = grp * TOK;
+        long long id = a.pad;
+        if (lane < TOK && m0 + lane < M) {
+            const long long m = m0 + lane;
+            id = a.ids[m];
             int p, be, ac;
-            route_token(a, b, s, id, p, be, ac);
+            route_token(a, (int)(m / a.S), (int)(m % a.S), id, p, be, ac);
             pos_idx[m] = p;
             beh_idx[m] = min(max(be, 0), a.n_beh);
             act_idx[m] = min(max(ac, 0), a.n_beh);
         }
         if (x != nullptr) {
-            const long long row = (id >= 0 && id < a.vocab) ? id : a.pad;
-            const bf16x8* src = reinterpret_cast<const bf16x8*>(table + row * H);
-            bf16x8* dst = reinterpret_cast<bf16x8*>(x + m * H);
-            for (int c = lane; c < H / 8; c += 32) dst[c] = src[c];
+            long long rows[TOK];
+#pragma unroll
+            for (int u = 0; u < TOK; ++u) {
+                const long long idu = __shfl_sync(0xffffffffu, id, u);
+                rows[u] = (idu >= 0 && idu < a.vocab) ? idu : a.pad;
+            }
+            for (int c = lane; c < H / 8; c += 32) {  // H = 256: exactly one pass, 16 B per lane
+                bf16x8 v[TOK];
+#pragma unroll
+                for (int u = 0; u < TOK; ++u) v[u] = *reinterpret_cast<const bf16x8*>(table + rows[u] * H + c * 8);
+#pragma unroll
+                for (int u = 0; u < TOK; ++u)
+                    if (m0 + u < M) *reinterpret_cast<bf16x8*>(x + (m0 + u) * H + c * 8) = v[u];
+            }
         }
     }
 }
@@ -281,31 +301,36 @@ __global__ void emb_reduce_kernel(const bf16* __restrict__ dx, int H, const int*
         const int v = lo;
         const int beg = bin_start[v] + (ch - chunk_start[v]) * EMB_CHUNK;
         const int end = min(beg + EMB_CHUNK, bin_start[v + 1]);
-        for (int c = lane; c < H / 8; c += 32) {  // H = 256: exactly one pass, 16 B per lane
+        // the chunk's (<= 64) row indices: two coalesced loads, broadcast by shuffle below
+        const int n = end - beg;
+        const int idx0 = (lane < n) ? sorted_rows[beg + lane] : 0;
+        const int idx1 = (32 + lane < n) ? sorted_rows[beg + 32 + lane] : 0;
+        for (int c0 = 0; c0 < H / 8; c0 += 32) {  // H = 256: exactly one pass, 16 B per lane
+            const int c = c0 + lane;
+            const bool col_ok = c < H / 8;
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            int i = beg;
-            for (; i + 4 <= end; i += 4) {
-                bf16x8 r[4];
+            for (int i = 0; i < n; i += 8) {      // 8 rows (4 KB per warp) in flight
+                bf16x8 r[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    r[u] = *reinterpret_cast<const bf16x8*>(dx + (long long)sorted_rows[i + u] * H + c * 8);
+                for (int u = 0; u < 8; ++u) {
+                    const int k = i + u;
+                    const int row = __shfl_sync(0xffffffffu, k < 32 ? idx0 : idx1, k & 31);
+                    r[u].u[0] = r[u].u[1] = r[u].u[2] = r[u].u[3] = 0u;
+                    if (k < n && col_ok) r[u] = *reinterpret_cast<const bf16x8*>(dx + (long long)row * H + c * 8);
+                }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     float f[8];
                     bf16x8_to_float(r[u], f);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) acc[k] += f[k];
                 }
             }
-            for (; i < end; ++i) {
-                float f[8];
-                bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dx + (long long)sorted_rows[i] * H + c * 8), f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += f[k];
-            }
             float* out = dtable + (long long)v * H + c * 8;
+            if (col_ok) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(out + k, acc[k]);
+                for (int k = 0; k < 8; ++k) atomicAdd(out + k, acc[k]);
+            }
         }
     }
 }
@@ -323,7 +348,8 @@ extern "C" int gamer_embed_route_fwd(const long long* ids, const long long* ctx,
     RouteArgs a{ids, ctx ? ctx : ids, ctx ? ctx_ld : (long long)S, B, S, pos0, tokens_per_item, pad, eos, vocab,
                 beh_lut, n_beh};
     const int threads = 256, wpb = threads / 32;
-    const int grid = (int)((M + wpb - 1) / wpb < 148 * 16 ? (M + wpb - 1) / wpb : 148 * 16);
+    const long long groups = (M + TOK - 1) / TOK;
+    const int grid = (int)((groups + wpb - 1) / wpb < 148 * 8 ? (groups + wpb - 1) / wpb : 148 * 8);
     embed_route_kernel<<<grid, threads, 0, stream>>>(a, reinterpret_cast<const bf16*>(table_bf16), H,
                                                      reinterpret_cast<bf16*>(x_bf16), pos_idx, beh_idx, act_idx);
     GAMER_LAUNCH_CHECK();

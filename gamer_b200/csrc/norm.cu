@@ -14,6 +14,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int H256 = 256;
 
+constexpr int NR = 2;  // rows per warp iteration: their loads are issued back to back (twice the bytes in flight)
+
 __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, float eps, long long M,
                                    bf16* __restrict__ out, long long ld_out, const int* __restrict__ row_map,
                                    const bf16* __restrict__ cat_table, const int* __restrict__ cat_idx, int cat_dim,
@@ -23,23 +25,40 @@ __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const float* __re
     float wv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) wv[i] = w[lane * 8 + i];
-    for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
-        float f[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8), f);
-        float ss = 0.f;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long m0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m0 < M; m0 += stride * NR) {
+        bf16x8 raw[NR];
+        long long orow[NR];
+        int cidx[NR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-        ss = warp_sum(ss);
-        const float rstd = rsqrtf(ss * (1.0f / H256) + eps);
-        if (lane == 0 && rstd_out != nullptr) rstd_out[m] = rstd;
-        const long long orow = row_map ? (long long)row_map[m] : m;
+        for (int r = 0; r < NR; ++r) {
+            const long long m = m0 + r * stride;     // warp-uniform
+            if (m < M) {
+                raw[r] = *reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8);
+                orow[r] = row_map ? (long long)row_map[m] : m;
+                cidx[r] = (cat_table != nullptr) ? cat_idx[m] : 0;
+            }
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = wv[i] * (f[i] * rstd);
-        bf16* op = out + orow * ld_out;
-        *reinterpret_cast<bf16x8*>(op + lane * 8) = float_to_bf16x8(f);
-        if (cat_table != nullptr && lane < cat_dim / 8) {
-            const bf16x8 e = *reinterpret_cast<const bf16x8*>(cat_table + (long long)cat_idx[m] * cat_dim + lane * 8);
-            *reinterpret_cast<bf16x8*>(op + H256 + lane * 8) = e;
+        for (int r = 0; r < NR; ++r) {
+            const long long m = m0 + r * stride;
+            if (m >= M) continue;
+            float f[8];
+            bf16x8_to_float(raw[r], f);
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+            ss = warp_sum(ss);
+            const float rstd = rsqrtf(ss * (1.0f / H256) + eps);
+            if (lane == 0 && rstd_out != nullptr) rstd_out[m] = rstd;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = wv[i] * (f[i] * rstd);
+            bf16* op = out + orow[r] * ld_out;
+            *reinterpret_cast<bf16x8*>(op + lane * 8) = float_to_bf16x8(f);
+            if (cat_table != nullptr && lane < cat_dim / 8) {
+                const bf16x8 e = *reinterpret_cast<const bf16x8*>(cat_table + (long long)cidx[r] * cat_dim + lane * 8);
+                *reinterpret_cast<bf16x8*>(op + H256 + lane * 8) = e;
+            }
         }
     }
 }
@@ -49,7 +68,7 @@ __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const float* __re
 //   dw   += sum_m dh*x*rstd        (block partials -> fp32 atomics)
 //   dcat[cat_idx[m]] += dh[m, H:H+cat_dim]
 template <bool HAS_CAT>
-__global__ void __launch_bounds__(256, HAS_CAT ? 3 : 4)
+__global__ void __launch_bounds__(256, HAS_CAT ? 2 : 3)
 rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ rstd_in, float eps, long long M,
                                    const bf16* __restrict__ dh, long long ld_dh, const int* __restrict__ row_map,
@@ -71,53 +90,74 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
         for (int q = 0; q < (HAS_CAT ? 4 : 1); ++q) catacc[q][i] = 0.f;
     }
-    for (long long m = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
-        float xf[8], df[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8), xf);
-        const long long srow = row_map ? (long long)row_map[m] : m;
-        const bf16* dp = dh + srow * ld_dh;
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + lane * 8), df);
-        float rstd;
-        if (rstd_in != nullptr) {
-            rstd = rstd_in[m];
-        } else {
-            float ss = 0.f;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long m0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); m0 < M; m0 += stride * NR) {
+        bf16x8 xr[NR], dr[NR], rr[NR], cr[NR];
+        float rs[NR];
+        int ci[NR];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ss += xf[i] * xf[i];
-            rstd = rsqrtf(warp_sum(ss) * (1.0f / H256) + eps);
+        for (int r = 0; r < NR; ++r) {                 // all loads of the NR rows first
+            const long long m = m0 + r * stride;        // warp-uniform
+            if (m < M) {
+                xr[r] = *reinterpret_cast<const bf16x8*>(x + m * H256 + lane * 8);
+                const long long srow = row_map ? (long long)row_map[m] : m;
+                const bf16* dp = dh + srow * ld_dh;
+                dr[r] = *reinterpret_cast<const bf16x8*>(dp + lane * 8);
+                if (dres != nullptr) rr[r] = *reinterpret_cast<const bf16x8*>(dres + m * H256 + lane * 8);
+                rs[r] = (rstd_in != nullptr) ? rstd_in[m] : 0.f;
+                if (HAS_CAT && lane < cat_dim / 8) {
+                    cr[r] = *reinterpret_cast<const bf16x8*>(dp + H256 + lane * 8);
+                    ci[r] = cat_idx[m];
+                }
+            }
         }
-        float dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dwacc[i] += df[i] * xf[i] * rstd;
-            df[i] *= wv[i];
-            dot += df[i] * xf[i];
-        }
-        dot = warp_sum(dot) * (1.0f / H256) * rstd * rstd * rstd;
-        float o[8];
+        for (int r = 0; r < NR; ++r) {
+            const long long m = m0 + r * stride;
+            if (m >= M) continue;
+            float xf[8], df[8];
+            bf16x8_to_float(xr[r], xf);
+            bf16x8_to_float(dr[r], df);
+            float rstd = rs[r];
+            if (rstd_in == nullptr) {
+                float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rstd * df[i] - xf[i] * dot;
-        if (dres != nullptr) {
-            float rf[8];
-            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dres + m * H256 + lane * 8), rf);
+                for (int i = 0; i < 8; ++i) ss += xf[i] * xf[i];
+                rstd = rsqrtf(warp_sum(ss) * (1.0f / H256) + eps);
+            }
+            float dot = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += rf[i];
-        }
-        *reinterpret_cast<bf16x8*>(dx + m * H256 + lane * 8) = float_to_bf16x8(o);
-        if (HAS_CAT && lane < cat_dim / 8) {
-            float cf[8];
-            bf16x8_to_float(*reinterpret_cast<const bf16x8*>(dp + H256 + lane * 8), cf);
-            const int r = cat_idx[m];
-            if (r < 4) {                       // register partials for the (<= 4) behaviour rows, flushed once below
+            for (int i = 0; i < 8; ++i) {
+                dwacc[i] += df[i] * xf[i] * rstd;
+                df[i] *= wv[i];
+                dot += df[i] * xf[i];
+            }
+            dot = warp_sum(dot) * (1.0f / H256) * rstd * rstd * rstd;
+            float o[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q == r) {
+            for (int i = 0; i < 8; ++i) o[i] = rstd * df[i] - xf[i] * dot;
+            if (dres != nullptr) {
+                float rf[8];
+                bf16x8_to_float(rr[r], rf);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) catacc[q][i] += cf[i];
-                    }
-            } else {
+                for (int i = 0; i < 8; ++i) o[i] += rf[i];
+            }
+            *reinterpret_cast<bf16x8*>(dx + m * H256 + lane * 8) = float_to_bf16x8(o);
+            if (HAS_CAT && lane < cat_dim / 8) {
+                float cf[8];
+                bf16x8_to_float(cr[r], cf);
+                const int rw = ci[r];
+                if (rw < 4) {                      // register partials for the (<= 4) behaviour rows, flushed once below
 #pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(&scat[r * cat_dim + lane * 8 + i], cf[i]);
+                    for (int q = 0; q < 4; ++q)
+                        if (q == rw) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) catacc[q][i] += cf[i];
+                        }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) atomicAdd(&scat[rw * cat_dim + lane * 8 + i], cf[i]);
+                }
             }
         }
     }
@@ -169,6 +209,25 @@ struct HeadArgs {
 struct HeadRow {
     float f[8];  // [0,4): first-half columns, [4,8): second-half columns
 };
+struct HeadRaw {
+    uint2 lo, hi;
+};
+__device__ __forceinline__ HeadRaw load_head_raw(const bf16* p, int sub) {
+    HeadRaw r;
+    r.lo = *reinterpret_cast<const uint2*>(p + 4 * sub);
+    r.hi = *reinterpret_cast<const uint2*>(p + 32 + 4 * sub);
+    return r;
+}
+__device__ __forceinline__ HeadRow head_row_from_raw(const HeadRaw& w) {
+    const uint2 lo = w.lo, hi = w.hi;
+    HeadRow r;
+    float2 t;
+    t = unpack_bf16(lo.x); r.f[0] = t.x; r.f[1] = t.y;
+    t = unpack_bf16(lo.y); r.f[2] = t.x; r.f[3] = t.y;
+    t = unpack_bf16(hi.x); r.f[4] = t.x; r.f[5] = t.y;
+    t = unpack_bf16(hi.y); r.f[6] = t.x; r.f[7] = t.y;
+    return r;
+}
 __device__ __forceinline__ HeadRow load_head_row(const bf16* p, int sub) {
     const uint2 lo = *reinterpret_cast<const uint2*>(p + 4 * sub);
     const uint2 hi = *reinterpret_cast<const uint2*>(p + 32 + 4 * sub);
@@ -209,11 +268,16 @@ qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
     const long long iters = (a.M + m_stride - 1) / m_stride;   // uniform trip count: shuffles run in full warps
     int pos = (int)(m0 % a.L);
     const int pstep = (int)(m_stride % a.L);
+    HeadRaw nxt = load_head_raw(raw + (m0 < a.M ? m0 : 0) * ld_raw + h * HD, sub);
     for (long long it = 0; it < iters; ++it) {
         const long long mm = m0 + it * m_stride;
         const bool live = mm < a.M;
         const long long m = live ? mm : 0;
-        HeadRow u = load_head_row(raw + m * ld_raw + h * HD, sub);
+        HeadRow u = head_row_from_raw(nxt);
+        {   // next token's row: in flight while this one is normalised and rotated
+            const long long mn = mm + m_stride;
+            nxt = load_head_raw(raw + (mn < a.M ? mn : 0) * ld_raw + h * HD, sub);
+        }
         if (HAS_EMB) {
             const HeadRow e = load_head_row(emb + (long long)a.act_idx[m] * width + hc, sub);
 #pragma unroll
@@ -286,12 +350,20 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
     const long long iters = (a.M + m_stride - 1) / m_stride;
     int pos = (int)(m0 % a.L);
     const int pstep = (int)(m_stride % a.L);
+    HeadRaw nu = load_head_raw(raw + (m0 < a.M ? m0 : 0) * ld_raw + h * HD, sub);
+    HeadRaw nd = load_head_raw(dout + (m0 < a.M ? m0 : 0) * ld_dout + h * HD, sub);
     for (long long it = 0; it < iters; ++it) {
         const long long mm = m0 + it * m_stride;
         const bool live = mm < a.M;
         const long long m = live ? mm : 0;
-        HeadRow u = load_head_row(raw + m * ld_raw + h * HD, sub);
-        const HeadRow d = load_head_row(dout + m * ld_dout + h * HD, sub);
+        HeadRow u = head_row_from_raw(nu);
+        const HeadRow d = head_row_from_raw(nd);
+        {   // next token's rows: in flight while this one is processed
+            const long long mn = mm + m_stride;
+            const long long mc = mn < a.M ? mn : 0;
+            nu = load_head_raw(raw + mc * ld_raw + h * HD, sub);
+            nd = load_head_raw(dout + mc * ld_dout + h * HD, sub);
+        }
         int act = 0;
         if (HAS_EMB) {
             act = live ? a.act_idx[m] : 0;
