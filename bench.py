@@ -220,11 +220,31 @@ def run_reference(args):
                              "sample": f"{rows} full-length rows (L={L}) per step: fwd+bwd+clip+AdamW, fp32, oracle port of "
                                        f"the reference's PyTorch path"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON result): everything libraries print to fd 1 on the way (NCCL's version
+    banner, ...) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -402,7 +422,7 @@ def main():
             line["cpu_baseline"] = {"value": rows / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"{rows} full-length rows (L={L}) per step x {n_cpu} steps after 1 warm-up: "
                                               f"fwd+bwd+clip+AdamW, fp32 oracle port"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

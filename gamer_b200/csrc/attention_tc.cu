@@ -1019,10 +1019,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         tc_fence_after();
                     }
                     trace_pt(p.tr, 0, tn, 5);
+                    umma_commit(&qdo_free[st]);   // Q / dO of this step are dead once dK is done: dQ reads dS and K only
                     issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false);     // dQ = dS K
                     umma_commit(&dq_full[db]);
                     umma_commit(ds_free);
-                    umma_commit(&qdo_free[st]);
                     if (n + 1 == N) {
                         umma_commit(dkv_full);
                         umma_commit(&kv_free[ks]);

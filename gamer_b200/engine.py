@@ -22,6 +22,9 @@ import torch
 from . import kernels as K
 
 BF16 = torch.bfloat16
+# backbones without the gated behaviour "cross" attention (one self-attention + routed FFN per layer,
+# `post_attention_layernorm`): Qwen3SessionMoe (session mask, session RoPE) and Qwen3Moe (train_MB_decoder: plain causal)
+NO_CROSS_VARIANTS = ("Qwen3SessionMoe", "Qwen3Moe")
 CE_CHUNK_ROWS = 32768
 V_ALIGN = 64
 
@@ -51,7 +54,7 @@ class Arch:
 
     @staticmethod
     def from_config(cfg, variant: str) -> "Arch":
-        cross = tuple(getattr(cfg, "cross_attention_decoder", ()) or ()) if variant != "Qwen3SessionMoe" else ()
+        cross = tuple(getattr(cfg, "cross_attention_decoder", ()) or ()) if variant not in NO_CROSS_VARIANTS else ()
         theta = getattr(cfg, "rope_theta", None)
         if theta is None:
             theta = (getattr(cfg, "rope_parameters", None) or {}).get("rope_theta", 1e6)
@@ -84,6 +87,8 @@ class Arch:
             return K.MASK_CAUSAL, K.MASK_MULTI_CROSS
         if self.variant == "Qwen3SessionMoe":
             return K.MASK_SESSION, None
+        if self.variant == "Qwen3Moe":              # HF causal + padding mask (Qwen3Moe/model.py:306-461)
+            return K.MASK_CAUSAL, None
         if self.variant == "Qwen3SessionMulti":
             return K.MASK_SESSION, K.MASK_SESSION_CROSS
         raise ValueError(self.variant)
@@ -95,7 +100,7 @@ class Arch:
 def param_names(arch: Arch):
     """State-dict keys in the order the engine consumes them (SURVEY.md §8(b) checkpoint contract)."""
     names = ["model.embed_tokens.weight"]
-    post = "post_attention_layernorm" if arch.variant == "Qwen3SessionMoe" else "post_cross_attention_layernorm"
+    post = "post_attention_layernorm" if arch.variant in NO_CROSS_VARIANTS else "post_cross_attention_layernorm"
     for l in range(arch.n_layers):
         p = f"model.layers.{l}."
         names += [p + "input_layernorm.weight"]
@@ -130,7 +135,7 @@ class Pack:
         self.emb_t = emb_t
         self.norm = W["model.norm.weight"].detach().float().contiguous()
         self.layers = []
-        post = "post_attention_layernorm" if a.variant == "Qwen3SessionMoe" else "post_cross_attention_layernorm"
+        post = "post_attention_layernorm" if a.variant in NO_CROSS_VARIANTS else "post_cross_attention_layernorm"
         for l in range(a.n_layers):
             p = f"model.layers.{l}."
             d = {}
@@ -566,7 +571,7 @@ def grad_buffers(arch: Arch, device, flat: torch.Tensor | None = None):
 def unfuse_grads(arch: Arch, G: dict) -> dict:
     """Fused gradient buffers -> {state-dict key: fp32 grad view}."""
     out = {"model.embed_tokens.weight": G["model.embed_tokens.weight"], "model.norm.weight": G["model.norm.weight"]}
-    post = "post_attention_layernorm" if arch.variant == "Qwen3SessionMoe" else "post_cross_attention_layernorm"
+    post = "post_attention_layernorm" if arch.variant in NO_CROSS_VARIANTS else "post_cross_attention_layernorm"
     q, kv, H, I = arch.q_w, arch.kv_w, arch.hidden, arch.inter
     for l in range(arch.n_layers):
         p, k = f"L{l}.", f"model.layers.{l}."

@@ -77,14 +77,14 @@ class _Layer(nn.Module):
         super().__init__()
         sparse = idx in cfg.sparse_layers_decoder
         inject = idx in cfg.behavior_injection_decoder
-        cross = variant != "Qwen3SessionMoe" and idx in (getattr(cfg, "cross_attention_decoder", None) or [])
+        cross = variant not in E.NO_CROSS_VARIANTS and idx in (getattr(cfg, "cross_attention_decoder", None) or [])
         self.self_attn = _Attention(cfg, is_cross=False)
         if cross:
             self.cross_attn = _Attention(cfg, is_cross=True)
             self.post_self_attention_layernorm = _Weight(cfg.hidden_size)
         self.mlp = _SparseMLP(cfg, sparse, inject)
         self.input_layernorm = _Weight(cfg.hidden_size)
-        if variant == "Qwen3SessionMoe":
+        if variant in E.NO_CROSS_VARIANTS:
             self.post_attention_layernorm = _Weight(cfg.hidden_size)
         else:
             self.post_cross_attention_layernorm = _Weight(cfg.hidden_size)
@@ -295,6 +295,13 @@ class Qwen3SessionMoeWithTemperature(_GamerCausalLM):
     """Drop-in for SeqRec.models.generative.Qwen3SessionMoe.Qwen3SessionMoeWithTemperature
     (Qwen3SessionMoe/model.py:590-735)."""
     VARIANT = "Qwen3SessionMoe"
+
+
+class Qwen3MoeWithTemperature(_GamerCausalLM):
+    """Drop-in for SeqRec.models.generative.Qwen3Moe.Qwen3MoeWithTemperature (Qwen3Moe/model.py:604-640), the backbone
+    of `train_MB_decoder` (multi-behaviour sequences without sessions): HF causal + padding mask, token-position RoPE,
+    position-routed expert FFN.  `session_ids` / `actions` are accepted and ignored, as the reference's **kwargs do."""
+    VARIANT = "Qwen3Moe"
 
 
 class Qwen3SessionMultiWithTemperature(_GamerCausalLM):

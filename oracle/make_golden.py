@@ -33,7 +33,7 @@ GRAD_SAMPLES = 64
 def tiny_config(variant: str, n_layers: int = 3):
     cfg = ref_shim.reference_config(variant, max_his_len=20, num_layers=n_layers)
     cfg.behavior_injection_decoder = [0]
-    if variant != "Qwen3SessionMoe":
+    if variant not in ("Qwen3SessionMoe", "Qwen3Moe"):
         cfg.cross_attention_decoder = [1, 2]
     return cfg
 
@@ -150,10 +150,14 @@ def main():
         "train_qwen3multi_numitems.pt": lambda: train_case(R, "Qwen3Multi", 43, 4, num_items=777),
         "train_qwen3sessionmoe.pt": lambda: train_case(R, "Qwen3SessionMoe", 44, 5),
         "train_qwen3sessionmulti.pt": lambda: train_case(R, "Qwen3SessionMulti", 45, 6),
+        "train_qwen3moe.pt": lambda: train_case(R, "Qwen3Moe", 47, 8),
         "decode_qwen3multi_lvl2.pt": lambda: decode_case(R, "Qwen3Multi", 42, 5, 2, 8),
         "decode_qwen3multi_lvl1.pt": lambda: decode_case(R, "Qwen3Multi", 46, 7, 1, 6),
     }
+    only = set(sys.argv[1:])                   # python -m oracle.make_golden [file.pt ...]: regenerate a subset
     for name, fn in jobs.items():
+        if only and name not in only:
+            continue
         obj = fn()
         path = os.path.join(GOLDEN, name)
         torch.save(obj, path)

@@ -33,7 +33,7 @@ MASK_SESSION_CROSS = 3   # Qwen3SessionMulti cross:    s[j]<s[i] & act[j]<act[i]
 @dataclass
 class Spec:
     """Architecture constants (config/s2s-models/*/config.json + train_SMB_decoder.py:321-360)."""
-    variant: str = "Qwen3Multi"            # Qwen3Multi | Qwen3SessionMoe | Qwen3SessionMulti
+    variant: str = "Qwen3Multi"            # Qwen3Multi | Qwen3SessionMoe | Qwen3SessionMulti | Qwen3Moe
     vocab_size: int = 1041
     hidden: int = 256
     n_q: int = 6
@@ -57,7 +57,8 @@ class Spec:
 
     @staticmethod
     def from_hf_config(cfg, variant: str, temperature: float = 1.0) -> "Spec":
-        cross = tuple(getattr(cfg, "cross_attention_decoder", ()) or ()) if variant != "Qwen3SessionMoe" else ()
+        cross = tuple(getattr(cfg, "cross_attention_decoder", ()) or ()) \
+            if variant not in ("Qwen3SessionMoe", "Qwen3Moe") else ()
         return Spec(
             variant=variant, vocab_size=cfg.vocab_size, hidden=cfg.hidden_size, n_q=cfg.num_attention_heads,
             n_kv=cfg.num_key_value_heads, head_dim=cfg.head_dim, inter=cfg.intermediate_size,
@@ -254,7 +255,7 @@ def backbone(spec: Spec, W: dict, ids, am, positions, rope_pos, self_allow, cros
             x = x + dropped(attention_block(spec, W, p + "cross_attn.", h, cos, sin, cross_allow, act_idx, True,
                                             None if c is None else c["cross"], zp(l, dm.SITE_CROSS_P)),
                             zh(l, dm.SITE_CROSS_OUT, spec.hidden))
-        post = "post_attention_layernorm.weight" if spec.variant == "Qwen3SessionMoe" else \
+        post = "post_attention_layernorm.weight" if spec.variant in ("Qwen3SessionMoe", "Qwen3Moe") else \
             "post_cross_attention_layernorm.weight"
         h = rmsnorm(x, W[p + post], spec.eps)
         x = x + dropped(routed_ffn(spec, W, p + "mlp.", h, pos_idx, beh_idx, l in spec.inject_layers,
@@ -268,6 +269,8 @@ def mask_kinds(spec: Spec):
         return MASK_CAUSAL, MASK_MULTI_CROSS
     if spec.variant == "Qwen3SessionMoe":
         return MASK_SESSION, None
+    if spec.variant == "Qwen3Moe":            # train_MB_decoder backbone: HF causal + padding mask (Qwen3Moe/model.py:306-461)
+        return MASK_CAUSAL, None
     if spec.variant == "Qwen3SessionMulti":
         return MASK_SESSION, MASK_SESSION_CROSS
     raise ValueError(spec.variant)

@@ -69,10 +69,13 @@ def load_reference():
     from SeqRec.models.generative.Qwen3Multi.model import Qwen3MultiWithTemperature
     from SeqRec.models.generative.Qwen3SessionMoe.model import Qwen3SessionMoeWithTemperature
     from SeqRec.models.generative.Qwen3SessionMulti.model import Qwen3SessionMultiWithTemperature
+    from SeqRec.models.generative.Qwen3Moe.model import MyQwen3MoeForCausalLM, Qwen3MoeWithTemperature
+    # 4.x-style list at Qwen3Moe/model.py:464; transformers 5.x expects {tied key: source key}
+    MyQwen3MoeForCausalLM._tied_weights_keys = {"lm_head.weight": "model.embed_tokens.weight"}
     from SeqRec.generation.trie import Trie, prefix_allowed_tokens_fn_by_last_token
     from SeqRec.evaluation import ranking
     return dict(Qwen3Multi=Qwen3MultiWithTemperature, Qwen3SessionMoe=Qwen3SessionMoeWithTemperature,
-                Qwen3SessionMulti=Qwen3SessionMultiWithTemperature, Trie=Trie,
+                Qwen3SessionMulti=Qwen3SessionMultiWithTemperature, Qwen3Moe=Qwen3MoeWithTemperature, Trie=Trie,
                 prefix_allowed_tokens_fn_by_last_token=prefix_allowed_tokens_fn_by_last_token,
                 ranking=ranking)
 

@@ -16,7 +16,7 @@ def load_golden(name):
 def spec_from_golden(g, temperature=1.0):
     c = g["config"]
     variant = g["variant"]
-    cross = tuple(c["cross_attention_decoder"]) if variant != "Qwen3SessionMoe" else ()
+    cross = tuple(c["cross_attention_decoder"]) if variant not in ("Qwen3SessionMoe", "Qwen3Moe") else ()
     return om.Spec(variant=variant, vocab_size=c["vocab_size"], hidden=c["hidden_size"], n_q=c["num_attention_heads"],
                    n_kv=c["num_key_value_heads"], head_dim=c["head_dim"], inter=c["intermediate_size"],
                    n_layers=c["num_hidden_layers"], beh_dim=c["behavior_embedding_dim"], n_behavior=c["num_behavior"],

@@ -25,7 +25,8 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.gamer_route_perm_workspace_bytes(7) == 7 * 8 * 2 * 4
 
 
-@pytest.mark.parametrize("name", ["train_qwen3multi.pt", "train_qwen3sessionmoe.pt", "train_qwen3sessionmulti.pt"])
+@pytest.mark.parametrize("name", ["train_qwen3multi.pt", "train_qwen3sessionmoe.pt", "train_qwen3sessionmulti.pt",
+                                  "train_qwen3moe.pt"])
 def test_drop_in_classes_hold_reference_state_dict(name):
     from tests.test_model_gpu import build_model
     from gamer_b200 import engine as E

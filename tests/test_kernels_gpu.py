@@ -422,3 +422,33 @@ def test_cross_entropy_fused():
     ref.backward()
     assert rel_err(dl[:, :V], lf.grad / 0.7) < 5e-3
     assert dl[:, V:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_attention_long_history(kind):
+    """BASELINE.json configs[4]: max_his_len = 500 (L = 2505, 20 key tiles) through the tcgen05 kernels, ragged rows."""
+    from oracle import oracle_model as om
+    k = _k()
+    torch.manual_seed(40 + kind)
+    B, L, nq, nkv, hd = 2, 2505, 6, 3, 64
+    M = B * L
+    am, act, sess = _attn_inputs(B, L, 31 + kind, kind == 2)
+    qkv = bf(torch.randn(M, 768, device=DEV))
+    scale = hd ** -0.5
+    i32 = lambda t: t.to(torch.int32).to(DEV).contiguous()
+    o, lse, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
+    allow = om.allow_matrix(kind, am, act, sess, 5).to(DEV)
+    qf = qkv.float().requires_grad_(True)
+    q = qf[:, :384].view(B, L, nq, hd).transpose(1, 2)
+    kk = qf[:, 384:576].view(B, L, nkv, hd).transpose(1, 2)
+    v = qf[:, 576:].view(B, L, nkv, hd).transpose(1, 2)
+    ref = om.masked_attention(q, kk, v, allow, scale).transpose(1, 2).reshape(M, nq * hd)
+    assert rel_err(o, ref) < 8e-3
+    d_o = bf(torch.randn(M, nq * hd, device=DEV))
+    ref.backward(d_o.float())
+    dqkv = torch.zeros(M, 768, dtype=torch.bfloat16, device=DEV)
+    k.attn_bwd(qkv, o, d_o, lse, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale, dqkv)
+    g = qf.grad
+    for name, sl in (("dq", slice(0, 384)), ("dk", slice(384, 576)), ("dv", slice(576, 768))):
+        e = rel_err(dqkv[:, sl], g[:, sl])
+        assert e < 2e-2, (name, e)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 CLASSES = {"Qwen3Multi": "Qwen3MultiWithTemperature", "Qwen3SessionMoe": "Qwen3SessionMoeWithTemperature",
-           "Qwen3SessionMulti": "Qwen3SessionMultiWithTemperature"}
+           "Qwen3SessionMulti": "Qwen3SessionMultiWithTemperature", "Qwen3Moe": "Qwen3MoeWithTemperature"}
 
 
 def build_model(g, temperature=None):
@@ -46,7 +46,8 @@ def rel_err(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
-TRAIN = ["train_qwen3multi.pt", "train_qwen3multi_numitems.pt", "train_qwen3sessionmoe.pt", "train_qwen3sessionmulti.pt"]
+TRAIN = ["train_qwen3multi.pt", "train_qwen3multi_numitems.pt", "train_qwen3sessionmoe.pt", "train_qwen3sessionmulti.pt",
+         "train_qwen3moe.pt"]
 
 
 @pytest.mark.parametrize("name", TRAIN)

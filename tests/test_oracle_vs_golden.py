@@ -8,7 +8,7 @@ from oracle import oracle_model as om
 from tests.helpers import load_golden, spec_from_golden, weights_from_golden
 
 TRAIN = ["train_qwen3multi.pt", "train_qwen3multi_numitems.pt", "train_qwen3sessionmoe.pt",
-         "train_qwen3sessionmulti.pt"]
+         "train_qwen3sessionmulti.pt", "train_qwen3moe.pt"]
 
 
 @pytest.mark.parametrize("name", TRAIN)
