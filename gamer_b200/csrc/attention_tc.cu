@@ -866,8 +866,21 @@ __device__ __forceinline__ void bwd_p_tile(uint32_t (&s)[32], const int4* mk4, i
     }
 }
 
+// byte-wise x >= t over the four bytes of a word (SWAR): bit 7 of every result byte is the comparison
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t x, uint32_t t) {
+    const uint32_t sum = (x & 0x7f7f7f7fu) + (0x80808080u - (t & 0x7fu) * 0x01010101u);   // bit 7: low 7 bits >= those of t
+    return (t & 0x80u) ? (x & sum) : (x | sum);
+}
+// 0xffffffff when bit 7 of byte K of w is set, else 0 (one PRMT: sign-replicating byte select)
+template <int K>
+__device__ __forceinline__ uint32_t byte_sign_mask(uint32_t w) {
+    return prmt(w, 0u, 0x8888u | (K * 0x1111u));
+}
+
 // With dropout (DROP): O = (P o Z) V, Z = keep / keep_prob.  dV += (P o Z)^T dO; dS = P o (Z o dP - dsum) with
-// dsum = rowsum(dO o O) unchanged.  Uniform rows carry no dropout (Z = 1), as in the forward.
+// dsum = rowsum(dO o O) unchanged.  Z = zs * keep: the keep bits are byte sign flags (SWAR compare of the Philox bytes)
+// expanded to AND masks by one PRMT each, zs multiplies dV once in its epilogue and enters dS through an FMA.
+// Uniform rows carry no dropout (keep = all, their P is stored divided by zs), as in the forward.
 template <int KIND, bool DROP>
 __global__ void __launch_bounds__(B_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -1093,68 +1106,76 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         bwd_p_tile<KIND, 0>(s, mk4, act_i, sess_i, wgi * 32, row, jbase, i, istart, p.scale_log2, lse_i, lim_u, p.inv_L);
                 }
                 trace_pt(tr, 1, tn, 23);
-                // keep bits of this thread's 32 (query, key) pairs; zs = 1 / keep probability (1 on uniform rows)
-                uint32_t keep = 0xffffffffu;
-                float zs = 1.f;
+                // keep flags: bit 7 of byte (c & 3) of kw[c >> 2] <-> (query, key column c) is kept
+                uint32_t kw[8];
+                const float zs = DROP ? drop.scale : 1.f;
+                const float zrow = (DROP && !uni) ? zs : 1.f;        // factor of dP in dS
+                const float pmul = (DROP && uni) ? 1.f / zs : 1.f;   // dV is multiplied by zs in its epilogue
                 if constexpr (DROP) {
-                    if (!uni) {
-                        keep = 0u;
-                        zs = drop.scale;
 #pragma unroll
-                        for (int cb = 0; cb < 2; ++cb) {
-                            const uint4 rnd = drop_attn16(drop, (uint32_t)(b * p.n_q + 2 * g + hh), (uint32_t)i,
-                                                          (uint32_t)((jbase >> 4) + cb));
-                            const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                keep |= ((((rw[e >> 2] >> (8 * (e & 3))) & 0xffu) >= drop.thresh) ? 1u : 0u) << (cb * 16 + e);
-                        }
+                    for (int cb = 0; cb < 2; ++cb) {
+                        const uint4 rnd = drop_attn16(drop, (uint32_t)(b * p.n_q + 2 * g + hh), (uint32_t)i,
+                                                      (uint32_t)((jbase >> 4) + cb));
+                        kw[4 * cb + 0] = uni ? 0x80808080u : bytes_ge(rnd.x, drop.thresh);
+                        kw[4 * cb + 1] = uni ? 0x80808080u : bytes_ge(rnd.y, drop.thresh);
+                        kw[4 * cb + 2] = uni ? 0x80808080u : bytes_ge(rnd.z, drop.thresh);
+                        kw[4 * cb + 3] = uni ? 0x80808080u : bytes_ge(rnd.w, drop.thresh);
                     }
                 }
                 if (step_n > 0) mbar_wait(p_free, (step_n - 1) & 1);
                 trace_pt(tr, 1, tn, 24);
+                // P leaves as bf16 pairs: the masked (and, on uniform rows, pre-divided) copy goes to smem for dV, the
+                // plain copy stays in 16 registers for dS — the fp32 tile dies here, which is what keeps this loop
+                // inside the 80-register budget of a 768-thread CTA
+                uint32_t pp[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = q * 8 + 2 * e;
-                        float p0 = __uint_as_float(s[c]), p1 = __uint_as_float(s[c + 1]);
+                        uint32_t p0 = s[c], p1 = s[c + 1];
+                        pp[c >> 1] = pack_bf16(__uint_as_float(p0), __uint_as_float(p1));
                         if constexpr (DROP) {
-                            p0 = ((keep >> c) & 1u) ? p0 * zs : 0.f;
-                            p1 = ((keep >> (c + 1)) & 1u) ? p1 * zs : 0.f;
+                            p0 &= (c & 2) ? byte_sign_mask<2>(kw[c >> 2]) : byte_sign_mask<0>(kw[c >> 2]);
+                            p1 &= (c & 2) ? byte_sign_mask<3>(kw[c >> 2]) : byte_sign_mask<1>(kw[c >> 2]);
+                            pk[e] = pack_bf16(__uint_as_float(p0) * pmul, __uint_as_float(p1) * pmul);
+                        } else {
+                            pk[e] = pp[c >> 1];
                         }
-                        pk[e] = pack_bf16(p0, p1);
                     }
                     sts128(sP + (((ch0 + q) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
-                // ---- dS = P o (dP - dsum)
+                // ---- dS = P o (zs * keep o dP - dsum), dP read in two 16-column halves
                 trace_pt(tr, 1, tn, 25);
                 mbar_wait(dp_full, step_n & 1);
                 tc_fence_after();
                 trace_pt(tr, 1, tn, 26);
                 if (step_n > 0) mbar_wait(ds_free, (step_n - 1) & 1);
                 trace_pt(tr, 1, tn, 27);
-                {
-                    uint32_t dp[32];
-                    tmem_ld_32x32(t_dp, dp);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t dp[16];
+                    tmem_ld_32x16(t_dp + half * 16, dp);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q2 = 0; q2 < 2; ++q2) {
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int c = q * 8 + 2 * e;
-                            float g0 = __uint_as_float(dp[c]), g1 = __uint_as_float(dp[c + 1]);
+                            const int cl = q2 * 8 + 2 * e;          // column within the half
+                            const int c = half * 16 + cl;
+                            uint32_t g0 = dp[cl], g1 = dp[cl + 1];
                             if constexpr (DROP) {
-                                g0 = ((keep >> c) & 1u) ? g0 * zs : 0.f;
-                                g1 = ((keep >> (c + 1)) & 1u) ? g1 * zs : 0.f;
+                                g0 &= (c & 2) ? byte_sign_mask<2>(kw[c >> 2]) : byte_sign_mask<0>(kw[c >> 2]);
+                                g1 &= (c & 2) ? byte_sign_mask<3>(kw[c >> 2]) : byte_sign_mask<1>(kw[c >> 2]);
                             }
-                            const float d0 = __uint_as_float(s[c]) * (g0 - dsum_i);
-                            const float d1 = __uint_as_float(s[c + 1]) * (g1 - dsum_i);
+                            const float2 pv = unpack_bf16(pp[c >> 1]);
+                            const float d0 = pv.x * fmaf(__uint_as_float(g0), zrow, -dsum_i);
+                            const float d1 = pv.y * fmaf(__uint_as_float(g1), zrow, -dsum_i);
                             pk[e] = pack_bf16(d0, d1);
                         }
-                        sts128(sDS + (((ch0 + q) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        sts128(sDS + (((ch0 + half * 2 + q2) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
                 trace_pt(tr, 1, tn, 28);
@@ -1222,7 +1243,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll 1
             for (int which = 0; which < 2; ++which) {
                 const uint32_t t_acc = tmem_base + lane_off + (which == 0 ? T_DK : T_DV);
-                const float mul = (which == 0) ? p.scale : 1.f;
+                const float mul = (which == 0) ? p.scale : (DROP ? p.drop.scale : 1.f);   // dV = zs * (P o keep)^T dO
                 uint32_t pk[32];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
