@@ -7,6 +7,8 @@
 // One persistent CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
 // warps 2..5 = epilogue (TMEM -> registers -> global).  4-stage smem ring, 2 TMEM accumulator stages so the
 // epilogue of tile t overlaps the MMAs of tile t+1.
+#include <stdlib.h>
+
 #include "sm100_ptx.cuh"
 
 using namespace sm100;
@@ -33,34 +35,35 @@ struct GemmParams {
     DropParams drop;     // dropout of alpha * A B^T before the residual add (mask indexed by output row, column)
 };
 
-constexpr int BLOCK_N = 128;
 constexpr int TILE16K = 128 * 64 * 2;  // one [128 x 64] bf16 (or [128 x 32] fp32) SWIZZLE_128B box
 
 // STAGED: the epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (fully coalesced; the residual tile is
 // TMA-loaded into the same staging buffer beforehand and updated in place).  !STAGED: per-thread row stores, needed when
 // output rows are scattered through `row_map`.
-template <bool OUT_F32, bool STAGED>
+// BN = tile width: 128, or 256 for the wide projections (N a multiple of 256, >= 512): per 128 x 128 of output a
+// 128 x 256 tile fetches 96 KB of operands instead of 128 KB, and operand fetch (TMA requests of 128-byte rows) is what
+// paces these K = 256..1024 GEMMs.  The epilogue always works in 128-column halves through two staging buffers.
+template <bool OUT_F32, bool STAGED, int BN>
 struct GemmCfg {
-    // bytes in flight bound these small-K GEMMs (a [128 x 256] tile pair is 128 KB, fetched with ~1.5 us of latency): the
-    // bf16 staged variant trades its third output staging buffer for a fifth operand stage
-    static constexpr int STAGES = STAGED ? (OUT_F32 ? 3 : 5) : 6;
+    static constexpr int STAGES = STAGED ? (OUT_F32 ? 3 : (BN == 256 ? 3 : 5)) : (BN == 256 ? 4 : 6);
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int C_BUFS = STAGED ? 2 : 0;
-    static constexpr int C_BYTES = BLOCK_M * BLOCK_N * (OUT_F32 ? 4 : 2);
+    static constexpr int C_BYTES = BLOCK_M * 128 * (OUT_F32 ? 4 : 2);   // one 128-column half
     static constexpr int OFF_C = STAGES * STAGE_BYTES;
     static constexpr int OFF_BAR = OFF_C + C_BUFS * C_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024 /*align*/;
 };
 
-template <bool OUT_F32, bool STAGED>
+template <bool OUT_F32, bool STAGED, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
-    using S = GemmCfg<OUT_F32, STAGED>;
+    using S = GemmCfg<OUT_F32, STAGED, BN>;
     constexpr int STAGES = S::STAGES;
-    constexpr int TMEM_COLS = 2 * BLOCK_N;
+    constexpr int TMEM_COLS = 2 * BN;
+    constexpr int HALVES = BN / 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -114,7 +117,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 1; g <= MAX_GROUPS; ++g) seg[g] = 0x7fffffff;
     }
-    const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.rows + BLOCK_M - 1) / BLOCK_M;
     const int total = n_tiles * m_tiles;
     const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -136,7 +139,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int row0 = m_blk * BLOCK_M;
                 if (row0 >= row_end) break;
                 const int g = group_of(row0);
-                const int brow = g * p.N + n_blk * BLOCK_N;
+                const int brow = g * p.N + n_blk * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
@@ -150,19 +153,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (has_resid) {
                     constexpr int NB = S::C_BUFS > 0 ? S::C_BUFS : 1;
-                    const int cbuf = tcount % NB;
-                    const uint32_t use = tcount / NB;
-                    mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
-                    uint8_t* sc = smem + S::OFF_C + cbuf * S::C_BYTES;
-                    mbar_expect_tx(&r_full[cbuf], 2 * TILE16K);
-                    tma_load_2d(sc, &tmR, &r_full[cbuf], n_blk * BLOCK_N, row0);
-                    tma_load_2d(sc + TILE16K, &tmR, &r_full[cbuf], n_blk * BLOCK_N + 64, row0);
+#pragma unroll
+                    for (int half = 0; half < HALVES; ++half) {
+                        const uint32_t hc = tcount * HALVES + half;
+                        const int cbuf = hc % NB;
+                        const uint32_t use = hc / NB;
+                        mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
+                        uint8_t* sc = smem + S::OFF_C + cbuf * S::C_BYTES;
+                        mbar_expect_tx(&r_full[cbuf], 2 * TILE16K);
+                        tma_load_2d(sc, &tmR, &r_full[cbuf], n_blk * BN + half * 128, row0);
+                        tma_load_2d(sc + TILE16K, &tmR, &r_full[cbuf], n_blk * BN + half * 128 + 64, row0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -172,7 +179,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (row0 >= row_end) break;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -210,20 +217,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_blk = t / n_tiles, n_blk = t % n_tiles;
             const int row0 = m_blk * BLOCK_M;
             if (row0 >= row_end) break;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
             if constexpr (STAGED) {
-                const int cbuf = tcount % S::C_BUFS;
-                const uint32_t use = tcount / S::C_BUFS;
+              constexpr int NB = S::C_BUFS > 0 ? S::C_BUFS : 1;
+#pragma unroll 1
+              for (int half = 0; half < HALVES; ++half) {
+                const uint32_t hc = tcount * HALVES + half;
+                const int cbuf = hc % NB;
+                const uint32_t use = hc / NB;
                 if (has_resid) mbar_wait(&r_full[cbuf], use & 1);
                 else mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
+                if (half == 0) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                }
                 const uint32_t sc = smem_u32(smem + S::OFF_C + cbuf * S::C_BYTES) + trow * 128;
                 const uint32_t sw = trow & 7;
+                const int col_half = n_blk * BN + half * 128;
 #pragma unroll
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
-                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_32x32(taddr + half * 128 + c * 32, r);
                     tmem_ld_wait();
                     if constexpr (OUT_F32) {
 #pragma unroll
@@ -240,7 +254,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]) * p.alpha;
                             if (drop.thresh)
-                                drop_apply8(drop, (uint32_t)(row0 + trow), (uint32_t)((n_blk * BLOCK_N + c * 32 + q * 8) >> 3), v);
+                                drop_apply8(drop, (uint32_t)(row0 + trow), (uint32_t)((col_half + c * 32 + q * 8) >> 3), v);
                             if (has_resid) {
                                 bf16x8 rv;
                                 lds128(addr, rv.u[0], rv.u[1], rv.u[2], rv.u[3]);
@@ -254,9 +268,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (half == HALVES - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
                 fence_proxy_async();
                 named_bar_sync(1, 128);
                 if (warp == 2 && lane == 0) {
@@ -265,14 +281,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint8_t* sbuf = smem + S::OFF_C + cbuf * S::C_BYTES;
 #pragma unroll
                     for (int bx = 0; bx < NBOX; ++bx)
-                        if (n_blk * BLOCK_N + bx * BOX_COLS < p.N)
-                            tma_store_2d(&tmC, sbuf + bx * TILE16K, n_blk * BLOCK_N + bx * BOX_COLS, row0);
+                        if (col_half + bx * BOX_COLS < p.N)
+                            tma_store_2d(&tmC, sbuf + bx * TILE16K, col_half + bx * BOX_COLS, row0);
                     bulk_commit();
-                    if (tcount > 0) {  // every store but the one just issued has been read out: recycle its buffer
+                    if (hc > 0) {  // every store but the one just issued has been read out: recycle its buffer
                         bulk_wait_read1();
-                        mbar_arrive(&c_free[(tcount - 1) % S::C_BUFS]);
+                        mbar_arrive(&c_free[(hc - 1) % NB]);
                     }
                 }
+              }
             } else {
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
@@ -280,11 +297,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 long long orow = -1;
                 if (row < row_end) orow = (p.row_map != nullptr) ? (long long)p.row_map[row] : (long long)row;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
+                for (int c = 0; c < BN; c += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c, r);
                     tmem_ld_wait();
-                    const int col0 = n_blk * BLOCK_N + c;
+                    const int col0 = n_blk * BN + c;
                     if (orow >= 0 && col0 < p.N) {
                         float v[32];
 #pragma unroll
@@ -626,17 +643,17 @@ int make_tmap_f32(CUtensorMap* m, const void* base, long long rows, long long co
     return 0;
 }
 
-template <bool OUT_F32, bool STAGED>
+template <bool OUT_F32, bool STAGED, int BN = 128>
 int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                    const GemmParams& p, cudaStream_t stream) {
-    using S = GemmCfg<OUT_F32, STAGED>;
-    auto kern = gemm_tn_kernel<OUT_F32, STAGED>;
+    using S = GemmCfg<OUT_F32, STAGED, BN>;
+    auto kern = gemm_tn_kernel<OUT_F32, STAGED, BN>;
     static bool configured = false;
     if (!configured) {
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
-    const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+    const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
     GAMER_LAUNCH_CHECK();
@@ -658,12 +675,20 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
                   "residual rows must be 16-byte aligned (ldr=%lld)", ldr);
     CUtensorMap tmA, tmB, tmC, tmR;
     if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;
-    if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, BLOCK_N)) return e;
+    // staged (TMA-store) epilogue whenever output rows are the A rows; fp32 outputs carry no residual in this code base
+    const bool staged = row_map == nullptr && !(c_is_f32 && resid != nullptr);
+    static int wide_min_n = -1;   // GAMER_GEMM_WIDE_MIN_N: smallest N that takes 128 x 256 tiles (tuning / A-B switch)
+    if (wide_min_n < 0) {
+        const char* e = getenv("GAMER_GEMM_WIDE_MIN_N");
+        wide_min_n = (e != nullptr && atoi(e) > 0) ? atoi(e) : 512;
+    }
+    // 128 x 256 tiles for the wide projections, and for the N = 256 dgrads with a long reduction and no residual tile
+    // (measured per shape with tools/gemm_bench.py; the residual GEMMs of width 256 are faster with 128 x 128 tiles)
+    const bool wide = staged && !c_is_f32 && N % 256 == 0 && (N >= wide_min_n || (resid == nullptr && K >= 768));
+    if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, wide ? 256 : 128)) return e;
     GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha,
                  make_drop(drop, 16)};
     GAMER_REQUIRE(p.drop.thresh == 0 || !c_is_f32, "dropout epilogue is implemented for bf16 outputs");
-    // staged (TMA-store) epilogue whenever output rows are the A rows; fp32 outputs carry no residual in this code base
-    const bool staged = row_map == nullptr && !(c_is_f32 && resid != nullptr);
     if (!staged) {
         tmC = tmA;
         tmR = tmA;
@@ -679,6 +704,7 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
     tmR = tmA;
     if (resid != nullptr)
         if (int e = make_tmap_bf16(&tmR, resid, rows, N, ldr, BLOCK_M)) return e;
+    if (wide) return launch_gemm_tn<false, true, 256>(tmA, tmB, tmC, tmR, p, stream);
     return launch_gemm_tn<false, true>(tmA, tmB, tmC, tmR, p, stream);
 }
 
