@@ -250,6 +250,29 @@ __device__ __forceinline__ float group8_sum(float v) {
     return v;
 }
 
+// Token ranges: block b owns a contiguous chunk of tokens and each of its Z slices a contiguous sub-chunk, which it
+// walks token by token — row pointers advance by one row stride, the RoPE position by one (mod L), and the behaviour
+// (action) index of a thread changes only every few tokens (items are 5 tokens long), so no 64-bit multiply, division or
+// per-token select survives in the loop.  Every slice runs the same trip count (`live` masks the tail) because a warp may
+// straddle slices when the head count is not a multiple of four.
+struct TokenRange {
+    long long begin, end;  // this slice's tokens
+    int iters;             // uniform trip count
+};
+__device__ __forceinline__ TokenRange slice_range(long long M, int Z, int z) {
+    const long long per_block = (M + gridDim.x - 1) / gridDim.x;
+    const long long per_z = (per_block + Z - 1) / Z;
+    const long long b0 = (long long)blockIdx.x * per_block;
+    TokenRange r;
+    r.begin = b0 + (long long)z * per_z;
+    long long e = r.begin + per_z;
+    if (e > b0 + per_block) e = b0 + per_block;
+    if (e > M) e = M;
+    r.end = e;
+    r.iters = (int)per_z;
+    return r;
+}
+
 template <bool HAS_EMB>
 __global__ void __launch_bounds__(384)
 qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_raw, bf16* __restrict__ out,
@@ -263,27 +286,26 @@ qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
     const float4 w_lo = *reinterpret_cast<const float4*>(wn + 4 * sub);
     const float4 w_hi = *reinterpret_cast<const float4*>(wn + 32 + 4 * sub);
     const float wv[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
-    const long long m_stride = (long long)gridDim.x * Z;
-    const long long m0 = (long long)blockIdx.x * Z + threadIdx.z;
-    const long long iters = (a.M + m_stride - 1) / m_stride;   // uniform trip count: shuffles run in full warps
-    int pos = (int)(m0 % a.L);
-    const int pstep = (int)(m_stride % a.L);
-    HeadRaw nxt = load_head_raw(raw + (m0 < a.M ? m0 : 0) * ld_raw + h * HD, sub);
-    for (long long it = 0; it < iters; ++it) {
-        const long long mm = m0 + it * m_stride;
-        const bool live = mm < a.M;
-        const long long m = live ? mm : 0;
+    const TokenRange tr = slice_range(a.M, Z, threadIdx.z);
+    const long long mlast = a.M - 1;
+    long long m = tr.begin;
+    const long long mc0 = m < a.M ? m : mlast;
+    const bf16* rp = raw + mc0 * ld_raw + h * HD;      // row of the NEXT load (clamped to the last token)
+    bf16* op = out + mc0 * ld_out + h * HD;
+    int pos = (int)(mc0 % a.L);
+    HeadRaw nxt = load_head_raw(rp, sub);
+    for (int it = 0; it < tr.iters; ++it, ++m) {
+        const bool live = m < tr.end;
         HeadRow u = head_row_from_raw(nxt);
-        {   // next token's row: in flight while this one is normalised and rotated
-            const long long mn = mm + m_stride;
-            nxt = load_head_raw(raw + (mn < a.M ? mn : 0) * ld_raw + h * HD, sub);
-        }
+        if (m + 1 <= mlast) rp += ld_raw;              // next token's row: in flight while this one is processed
+        nxt = load_head_raw(rp, sub);
+        const long long mi = m <= mlast ? m : mlast;
         if (HAS_EMB) {
-            const HeadRow e = load_head_row(emb + (long long)a.act_idx[m] * width + hc, sub);
+            const HeadRow e = load_head_row(emb + (long long)a.act_idx[mi] * width + hc, sub);
 #pragma unroll
             for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
-        const int p = a.pos_ids ? a.pos_ids[m] : (live ? pos : 0) + a.pos0;
+        const int p = a.pos_ids ? a.pos_ids[mi] : pos + a.pos0;
         const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
         const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
         const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -303,15 +325,16 @@ qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = u.f[i];
         }
-        if (live) store_head_row(out + m * ld_out + h * HD, sub, o);
-        pos += pstep;
-        if (pos >= a.L) pos -= a.L;
+        if (live) store_head_row(op, sub, o);
+        op += ld_out;
+        if (++pos == a.L) pos = 0;
     }
 }
 
 // backward: d_out (grad wrt rotated q,k and v) -> d_raw; accumulates d qn_w / d kn_w and the behaviour-embedding grads.
-// A thread keeps ONE head for the whole kernel, so the norm-weight and behaviour-embedding partial sums live in
-// registers ([emb_rows <= 4][8 columns] per lane) and are flushed once per thread: no per-token atomics.
+// A thread keeps ONE head for the whole kernel: the norm-weight partial sums live in registers and are flushed once;
+// the behaviour-embedding partial sum is ONE register row for the current action index, flushed to shared memory when
+// the index changes (every few tokens along the thread's contiguous range) — no per-token atomics or selects.
 constexpr int MAX_EMB_ROWS = 4;
 
 template <bool HAS_EMB>
@@ -339,39 +362,46 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
     const float4 w_hi = *reinterpret_cast<const float4*>(wn + 32 + 4 * sub);
     const float wv[8] = {w_lo.x, w_lo.y, w_lo.z, w_lo.w, w_hi.x, w_hi.y, w_hi.z, w_hi.w};
     float dwn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float demb[HAS_EMB ? MAX_EMB_ROWS : 1][8];
+    float demb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cur_act = -1;
+    // columns of this thread within the head: 4*sub + i (i < 4), 32 + 4*sub + (i - 4)
+    auto flush_emb = [&]() {
+        if (cur_act >= 0 && cur_act < emb_rows) {
 #pragma unroll
-    for (int r = 0; r < (HAS_EMB ? MAX_EMB_ROWS : 1); ++r)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) demb[r][i] = 0.f;
+            for (int i = 0; i < 8; ++i)
+                atomicAdd(&semb[cur_act * emb_w + h * HD + (i < 4 ? 4 * sub + i : 28 + 4 * sub + i)], demb[i]);
+        }
+    };
 
-    const long long m_stride = (long long)gridDim.x * Z;
-    const long long m0 = (long long)blockIdx.x * Z + threadIdx.z;
-    const long long iters = (a.M + m_stride - 1) / m_stride;
-    int pos = (int)(m0 % a.L);
-    const int pstep = (int)(m_stride % a.L);
-    HeadRaw nu = load_head_raw(raw + (m0 < a.M ? m0 : 0) * ld_raw + h * HD, sub);
-    HeadRaw nd = load_head_raw(dout + (m0 < a.M ? m0 : 0) * ld_dout + h * HD, sub);
-    for (long long it = 0; it < iters; ++it) {
-        const long long mm = m0 + it * m_stride;
-        const bool live = mm < a.M;
-        const long long m = live ? mm : 0;
+    const TokenRange tr = slice_range(a.M, Z, threadIdx.z);
+    const long long mlast = a.M - 1;
+    long long m = tr.begin;
+    const long long mc0 = m < a.M ? m : mlast;
+    const bf16* rp = raw + mc0 * ld_raw + h * HD;
+    const bf16* dp = dout + mc0 * ld_dout + h * HD;
+    bf16* wp = draw + mc0 * ld_draw + h * HD;
+    int pos = (int)(mc0 % a.L);
+    HeadRaw nu = load_head_raw(rp, sub);
+    HeadRaw nd = load_head_raw(dp, sub);
+    for (int it = 0; it < tr.iters; ++it, ++m) {
+        const bool live = m < tr.end;
         HeadRow u = head_row_from_raw(nu);
         const HeadRow d = head_row_from_raw(nd);
-        {   // next token's rows: in flight while this one is processed
-            const long long mn = mm + m_stride;
-            const long long mc = mn < a.M ? mn : 0;
-            nu = load_head_raw(raw + mc * ld_raw + h * HD, sub);
-            nd = load_head_raw(dout + mc * ld_dout + h * HD, sub);
+        if (m + 1 <= mlast) {   // next token's rows: in flight while this one is processed
+            rp += ld_raw;
+            dp += ld_dout;
         }
+        nu = load_head_raw(rp, sub);
+        nd = load_head_raw(dp, sub);
+        const long long mi = m <= mlast ? m : mlast;
         int act = 0;
         if (HAS_EMB) {
-            act = live ? a.act_idx[m] : 0;
+            act = a.act_idx[mi];
             const HeadRow e = load_head_row(emb + (long long)act * width + hc, sub);
 #pragma unroll
             for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
-        const int p = a.pos_ids ? a.pos_ids[m] : (live ? pos : 0) + a.pos0;
+        const int p = a.pos_ids ? a.pos_ids[mi] : pos + a.pos0;
         const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
         const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
         const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -395,9 +425,10 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
         }
         dot = group8_sum(dot) * (1.0f / HD) * rstd * rstd * rstd;
         if (is_q || is_k) {
+            const float lr = live ? rstd : 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                dwn[i] += live ? dn[i] * u.f[i] * rstd : 0.f;
+                dwn[i] += dn[i] * u.f[i] * lr;
                 du[i] = rstd * du[i] - u.f[i] * dot;
             }
         } else {
@@ -405,32 +436,25 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
             for (int i = 0; i < 8; ++i) du[i] = d.f[i];
         }
         if (live) {
-            store_head_row(draw + m * ld_draw + h * HD, sub, du);
+            store_head_row(wp, sub, du);
             if (HAS_EMB) {
+                if (act != cur_act) {
+                    flush_emb();
+                    cur_act = act;
 #pragma unroll
-                for (int r = 0; r < MAX_EMB_ROWS; ++r)
-                    if (r == act) {
+                    for (int i = 0; i < 8; ++i) demb[i] = 0.f;
+                }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) demb[r][i] += du[i];
-                    }
+                for (int i = 0; i < 8; ++i) demb[i] += du[i];
             }
         }
-        pos += pstep;
-        if (pos >= a.L) pos -= a.L;
+        wp += ld_draw;
+        if (++pos == a.L) pos = 0;
     }
-    // this thread's columns within the head: 4*sub + i (i < 4), 32 + 4*sub + (i - 4)
+    if (HAS_EMB) flush_emb();
     if (is_q || is_k) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(&sdw[(is_q ? 0 : HD) + (i < 4 ? 4 * sub + i : 28 + 4 * sub + i)], dwn[i]);
-    }
-    if (HAS_EMB) {
-#pragma unroll
-        for (int r = 0; r < MAX_EMB_ROWS; ++r)
-            if (r < emb_rows) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    atomicAdd(&semb[r * emb_w + h * HD + (i < 4 ? 4 * sub + i : 28 + 4 * sub + i)], demb[r][i]);
-            }
     }
     __syncthreads();
     for (int i = tid; i < HD; i += nthr) {
