@@ -377,6 +377,15 @@ def main():
             ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None}
+        try:   # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
+            if tr:
+                roof["traffic"] = tr["bytes_per_launch"]
+                roof["traffic_unit"] = "bytes/launch"
+                roof["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         roof["peak_source"] = peak_src
         roof["share_of_step"] = top["ms"] / step_ms
         roof["avg_launch_ms"] = top["ms"] / max(1, top["calls"])
