@@ -39,6 +39,13 @@ class BucketReducer:
         s, e = self.ranges[name]
         self.pending.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def launch_flat(self):
+        """The whole buffer in one collective (used when the backward ran as a CUDA graph: nothing left to overlap
+        with, so per-bucket launches would only add latency)."""
+        if self.world == 1:
+            return
+        self.pending.append(dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
     def launch_all_reverse(self):
         for name in reversed(self.order):
             self.launch(name)

@@ -84,6 +84,7 @@ class NativeTrainer:
         self.max_graphs = max_graphs
         self.graphs = {}                   # shape key -> captured micro-batch (fwd + bwd)
         self.seen = {}                     # shape key -> eager runs so far (capture on the second occurrence)
+        self.opt_graph, self.opt_eager_runs = None, 0
         self.drop_off = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side dropout offset, +1 per micro-batch
         self.micro_batches = 0
 
@@ -165,7 +166,7 @@ class NativeTrainer:
         s_inv.copy_(inv_norm)
         g.replay()
         if last_micro:
-            self.reducer.launch_all_reverse()
+            self.reducer.launch_flat()             # one all-reduce over the whole flat gradient buffer
         return loss.clone()
 
     def step(self, batch, micro_batch=None):
@@ -186,13 +187,33 @@ class NativeTrainer:
         return total
 
     def optimizer_step(self):
-        n = self.flat_p.numel()
+        """clip + AdamW + bf16 operand refresh.  Step-dependent scalars (lr, bias corrections) travel through a small
+        device tensor, so with CUDA graphs the ~70 launches of this method are captured once and replayed."""
         self.step_idx += 1
         t = self.step_idx
         self.hp_host[0] = self.current_lr()
         self.hp_host[1] = 1.0 - self.betas[0] ** t
         self.hp_host[2] = 1.0 - self.betas[1] ** t
         self.hp.copy_(self.hp_host, non_blocking=True)
+        if not self.use_cuda_graphs:
+            self._optimizer_kernels()
+        elif self.opt_graph is None:
+            if self.opt_eager_runs < 1:            # first call eager: configures the kernels, and is the warm-up
+                self.opt_eager_runs += 1
+                self._optimizer_kernels()
+            else:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._optimizer_kernels()
+                self.opt_graph = g
+                g.replay()
+        else:
+            self.opt_graph.replay()
+        self.model._pack = None                    # the kernel wrote the weights behind autograd's back
+
+    def _optimizer_kernels(self):
+        n = self.flat_p.numel()
         gn = None
         if self.max_grad_norm and self.max_grad_norm > 0:
             self.gnorm_sq.zero_()
@@ -202,4 +223,3 @@ class NativeTrainer:
              ptr(self.decay_mask), ptr(self.flat_bf16), n, ptr(self.hp), self.betas[0], self.betas[1], self.eps,
              self.wd, ptr(gn), float(self.max_grad_norm or 0.0), 1.0 / self.world, _stream())
         self.pack.refresh()                        # in place: operands keep their addresses (captured graphs stay valid)
-        self.model._pack = None                    # the kernel wrote the weights behind autograd's back

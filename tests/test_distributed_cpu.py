@@ -34,8 +34,14 @@ def _worker(rank, world, port, ret):
         for k, v in named.items():
             v.copy_(W[k].grad if W[k].grad is not None else torch.zeros_like(W[k]))
         red = BucketReducer(flat, E.layer_ranges(arch))
+        local = flat.clone()
         red.launch_all_reverse()
         red.wait_all()
+        bucketed = flat.clone()
+        flat.copy_(local)                     # the single-collective path (CUDA-graph mode) reduces to the same sums
+        red.launch_flat()
+        red.wait_all()
+        assert torch.allclose(flat, bucketed, rtol=1e-6, atol=1e-8)
         flat /= world
         if rank == 0:
             # single-process equivalent: mean over ranks of the per-shard mean losses
