@@ -1283,38 +1283,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 __global__ void attn_tc_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ld_o, int B,
                                         int L, int Lp, int n_q, const float* __restrict__ lse, float* __restrict__ dsum_p,
                                         float* __restrict__ lse_p, unsigned* __restrict__ uni_bits) {
-    const long long total = (long long)B * Lp * n_q;
+    // grid = (groups of one sequence / 32, B); 8 threads per (padded row, head) group, 32-bit index math only
+    const int b = blockIdx.y;
     const int sub = threadIdx.x & 7;
-    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const long long gs = ((long long)gridDim.x * blockDim.x) >> 3;
-    const long long iters = (total + gs - 1) / gs;
-    for (long long it = 0; it < iters; ++it) {
-        const long long gi = g0 + it * gs;
-        const bool live = gi < total;
-        const long long prow = live ? gi / n_q : 0;     // padded row index b * Lp + i
-        const int h = live ? (int)(gi % n_q) : 0;
-        const int b = (int)(prow / Lp), i = (int)(prow % Lp);
-        const bool real = live && i < L;
-        const long long row = real ? (long long)b * L + i : 0;
-        float a[8], d[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8), a);
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8), d);
-        float s = 0.f;
+    const int grp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);   // (row i, head h) of sequence b
+    const bool live = grp < Lp * n_q;
+    const int i = live ? grp / n_q : 0;
+    const int h = live ? grp - i * n_q : 0;
+    const bool real = live && i < L;
+    const long long row = real ? (long long)b * L + i : 0;
+    float a[8], d[8];
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8), a);
+    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8), d);
+    float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += a[k] * d[k];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (live && sub == 0) {
-            const long long pi = ((long long)b * n_q + h) * Lp + i;
-            float ls = INFINITY;
-            if (real) {
-                ls = lse[((long long)b * n_q + h) * L + i];
-                if (h == 0 && ls == INFINITY) atomicOr(&uni_bits[b], 1u << (i / BT));
-            }
-            dsum_p[pi] = real ? s : 0.f;
-            lse_p[pi] = ls;
+    for (int k = 0; k < 8; ++k) s += a[k] * d[k];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live && sub == 0) {
+        const long long pi = ((long long)b * n_q + h) * Lp + i;
+        float ls = INFINITY;
+        if (real) {
+            ls = lse[((long long)b * n_q + h) * L + i];
+            if (h == 0 && ls == INFINITY) atomicOr(&uni_bits[b], 1u << (i / BT));
         }
+        dsum_p[pi] = real ? s : 0.f;
+        lse_p[pi] = ls;
     }
 }
 
@@ -1563,9 +1558,8 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     // uni bits and the dQ accumulator are adjacent: one memset
     GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)(bl.off_acc - bl.off_uni) + (size_t)bl.acc_bytes, stream));
     {
-        const long long groups = (long long)B * bl.ml.Lp * n_q;
-        const long long blocks = (groups * 8 + 255) / 256;
-        attn_tc_bwd_prep_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(
+        const dim3 grid((bl.ml.Lp * n_q * 8 + 255) / 256, B);
+        attn_tc_bwd_prep_kernel<<<grid, 256, 0, stream>>>(
             reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), ld_o, B, L, bl.ml.Lp, n_q, lse, dsum, lse_p,
             uni);
         GAMER_LAUNCH_CHECK();

@@ -161,6 +161,9 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long ld_sr
 // fused softmax cross-entropy over fp32 logits rows: one warp per row.
 //   loss_row[r] = lse - logit[label] (0 when label == ignore);  dlogits[r, :] = (softmax - onehot) * scale (bf16; columns
 //   [V, ld_d) zero-filled so the buffer can feed TMA-tiled GEMMs).  scale = grad_scale * (*inv_norm).
+// REG_COLS > 0: the row (V <= 32 * REG_COLS logits) is read from HBM once and kept in registers for the three steps (max,
+// sum of exponentials, gradient); REG_COLS == 0: generic three-pass version for larger vocabularies.
+template <int REG_COLS>
 __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long long* __restrict__ labels,
                                   long long R, int V, int ignore_index, const float* __restrict__ inv_norm,
                                   float grad_scale, float* __restrict__ loss_row, bf16* __restrict__ dlogits,
@@ -172,21 +175,58 @@ __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld
         const float* lp = logits + r * ld_l;
         const long long lab = labels[r];
         const bool valid = lab != ignore_index;
-        float mx = -INFINITY;
-        for (int c = lane; c < V; c += 32) mx = fmaxf(mx, lp[c]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int c = lane; c < V; c += 32) se += expf(lp[c] - mx);
-        se = warp_sum(se);
-        const float lse = mx + logf(se);
-        if (lane == 0) loss_row[r] = valid ? (lse - lp[lab]) : 0.f;
-        if (dlogits != nullptr) {
-            bf16* dp = dlogits + r * ld_d;
-            const float inv = valid ? scale / se : 0.f;
-            for (int c = lane; c < ld_d; c += 32) {
-                float v = 0.f;
-                if (c < V && valid) v = expf(lp[c] - mx) * inv - ((c == lab) ? scale : 0.f);
-                dp[c] = __float2bfloat16(v);
+        if constexpr (REG_COLS > 0) {
+            float v[REG_COLS];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < REG_COLS; ++k) {
+                const int c = lane + 32 * k;
+                v[k] = (c < V) ? lp[c] : -INFINITY;
+                mx = fmaxf(mx, v[k]);
+            }
+            mx = warp_max(mx);
+            float se = 0.f, at_label = 0.f;
+#pragma unroll
+            for (int k = 0; k < REG_COLS; ++k) {
+                const int c = lane + 32 * k;
+                if (c == lab) at_label = v[k];
+                v[k] = expf(v[k] - mx);          // exp(-inf) = 0 on the padding columns
+                se += v[k];
+            }
+            se = warp_sum(se);
+            at_label = warp_sum(at_label);
+            if (lane == 0) loss_row[r] = valid ? (mx + logf(se) - at_label) : 0.f;
+            if (dlogits != nullptr) {
+                bf16* dp = dlogits + r * ld_d;
+                const float inv = valid ? scale / se : 0.f;
+#pragma unroll
+                for (int k = 0; k < REG_COLS; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < ld_d) {
+                        float g = 0.f;
+                        if (c < V && valid) g = v[k] * inv - ((c == lab) ? scale : 0.f);
+                        dp[c] = __float2bfloat16(g);
+                    }
+                }
+                for (int c = lane + 32 * REG_COLS; c < ld_d; c += 32) dp[c] = __float2bfloat16(0.f);
+            }
+        } else {
+            float mx = -INFINITY;
+            for (int c = lane; c < V; c += 32) mx = fmaxf(mx, lp[c]);
+            mx = warp_max(mx);
+            float se = 0.f;
+            for (int c = lane; c < V; c += 32) se += expf(lp[c] - mx);
+            se = warp_sum(se);
+            const float lse = mx + logf(se);
+            if (lane == 0) loss_row[r] = valid ? (lse - lp[lab]) : 0.f;
+            if (dlogits != nullptr) {
+                bf16* dp = dlogits + r * ld_d;
+                const float inv = valid ? scale / se : 0.f;
+                for (int c = lane; c < ld_d; c += 32) {
+                    float v = 0.f;
+                    if (c < V && valid) v = expf(lp[c] - mx) * inv - ((c == lab) ? scale : 0.f);
+                    dp[c] = __float2bfloat16(v);
+                }
             }
         }
     }
@@ -274,8 +314,12 @@ extern "C" int gamer_ce_fwd_bwd(const float* logits, long long ld_l, const long 
     if (R == 0) return 0;
     const int wpb = 8;
     const int grid = (int)((R + wpb - 1) / wpb < 148 * 8 ? (R + wpb - 1) / wpb : 148 * 8);
-    ce_fwd_bwd_kernel<<<grid, wpb * 32, 0, stream>>>(logits, ld_l, labels, R, V, ignore_index, inv_norm, grad_scale,
-                                                     loss_row, reinterpret_cast<bf16*>(dlogits), ld_d);
+    if (V <= 32 * 36)
+        ce_fwd_bwd_kernel<36><<<grid, wpb * 32, 0, stream>>>(logits, ld_l, labels, R, V, ignore_index, inv_norm, grad_scale,
+                                                             loss_row, reinterpret_cast<bf16*>(dlogits), ld_d);
+    else
+        ce_fwd_bwd_kernel<0><<<grid, wpb * 32, 0, stream>>>(logits, ld_l, labels, R, V, ignore_index, inv_norm, grad_scale,
+                                                            loss_row, reinterpret_cast<bf16*>(dlogits), ld_d);
     GAMER_LAUNCH_CHECK();
     return 0;
 }

@@ -613,9 +613,11 @@ def unfuse_grads(arch: Arch, G: dict) -> dict:
     return out
 
 
-def lm_head_backward(arch: Arch, pack: Pack, hidden, shifted, scale_dev, temperature, d_emb):
+def lm_head_backward(arch: Arch, pack: Pack, hidden, shifted, scale_dev, temperature, d_emb, loss_sum=None):
     """Recompute the logits chunk by chunk, emit dlogits (already scaled by grad_out * inv_norm / T), and run the
-    lm_head dgrad + wgrad.  Returns d_hidden [M,H] bf16; accumulates the tied-weight gradient into d_emb."""
+    lm_head dgrad + wgrad.  Returns d_hidden [M,H] bf16; accumulates the tied-weight gradient into d_emb.  The fused CE
+    kernel produces the per-row losses in the same pass: when `loss_sum` (fp32 scalar tensor) is given they are added
+    to it, so a caller that always runs forward and backward together (the native trainer) skips the forward head."""
     M = hidden.shape[0]
     dev = hidden.device
     d_hidden = torch.empty(M, arch.hidden, dtype=BF16, device=dev)
@@ -626,33 +628,39 @@ def lm_head_backward(arch: Arch, pack: Pack, hidden, shifted, scale_dev, tempera
         r1 = min(M, r0 + CE_CHUNK_ROWS)
         n = r1 - r0
         K.gemm_tn(hidden[r0:r1], pack.emb, arch.vocab, out=buf[:n], alpha=1.0 / temperature)
-        K.ce_fwd_bwd(buf[:n], shifted[r0:r1], arch.vocab, scale_dev, 1.0 / temperature, dlogits=dl[:n])
+        loss_row = K.ce_fwd_bwd(buf[:n], shifted[r0:r1], arch.vocab, scale_dev, 1.0 / temperature, dlogits=dl[:n])
+        if loss_sum is not None:
+            loss_sum += loss_row.sum()
         K.gemm_tn(dl[:n, :arch.vocab], pack.emb_t[:, :arch.vocab], arch.hidden, K=arch.vocab, out=d_hidden[r0:r1])
         K.gemm_wgrad(dl[:n, :arch.vocab], hidden[r0:r1], arch.vocab, arch.hidden,
                      d_emb.view(1, arch.vocab, arch.hidden))
     return d_hidden
 
 
-def loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, drop: DropCtx | None = None):
-    """Forward of the training step.  Returns (loss, state for `loss_backward`)."""
+def loss_forward(arch, pack, meta, lut, input_ids, shifted, inv_norm, temperature, drop: DropCtx | None = None,
+                 defer_loss: bool = False):
+    """Forward of the training step.  Returns (loss, state for `loss_backward`).  defer_loss=True skips the lm_head +
+    CE forward: `loss_backward` then returns the loss from its own (fused forward + backward) pass over the logits."""
     hidden, saved = forward_stack(arch, pack, input_ids, meta, lut, save=True, drop=drop)
-    loss = lm_head_loss(arch, pack, hidden, shifted, inv_norm, temperature)
+    loss = None if defer_loss else lm_head_loss(arch, pack, hidden, shifted, inv_norm, temperature)
     sort_buf = K.embed_sort(input_ids.view(-1), arch.vocab, arch.pad)
     return loss, dict(saved=saved, hidden=hidden, shifted=shifted, inv_norm=inv_norm, temperature=temperature,
-                      sort_buf=sort_buf, meta=meta, drop=drop)
+                      sort_buf=sort_buf, meta=meta, drop=drop, defer_loss=defer_loss)
 
 
 def loss_backward(arch, pack, st, grad_out, G, on_layer_done=None):
     """Backward of the training step into the fused gradient buffers G (accumulating).  grad_out: device scalar."""
     scale = (grad_out.float().reshape(()) * st["inv_norm"].view(())).reshape(1).contiguous()
+    loss_sum = torch.zeros((), dtype=torch.float32, device=st["hidden"].device) if st.get("defer_loss") else None
     d_hidden = lm_head_backward(arch, pack, st["hidden"], st["shifted"], scale, st["temperature"],
-                                G["model.embed_tokens.weight"])
+                                G["model.embed_tokens.weight"], loss_sum=loss_sum)
     dx0 = backward_stack(arch, pack, st["meta"], st["saved"], d_hidden, G, on_layer_done=on_layer_done,
                          drop=st.get("drop"))
     K.embed_bwd(dx0, arch.vocab, st["sort_buf"], G["model.embed_tokens.weight"])
     if on_layer_done is not None:
         on_layer_done(-1)
     st["saved"] = None
+    return None if loss_sum is None else loss_sum * st["inv_norm"].view(())
 
 
 class DecoderLossFunction(torch.autograd.Function):

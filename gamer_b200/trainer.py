@@ -120,11 +120,12 @@ class NativeTrainer:
         meta = E.make_meta(a, ids, batch.get("attention_mask"), batch.get("actions"), batch.get("session_ids"),
                            batch.get("extended_session_ids"))
         shifted = E.shift_labels(batch["labels"])
-        loss, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature),
-                                  drop=self._drop_ctx())
+        # forward and backward always run together here: the loss comes out of the backward's fused CE pass, and the
+        # forward lm_head GEMM + CE (a second pass over the [M, V] logits) is skipped
+        _, st = E.loss_forward(a, self.pack, meta, self.lut, ids, shifted, inv_norm, float(self.model.temperature),
+                               drop=self._drop_ctx(), defer_loss=True)
         one = torch.ones((), dtype=torch.float32, device=self.dev)
-        E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=hook)
-        return loss
+        return E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=hook)
 
     def _graph_key(self, batch):
         cfg = self.model._drop_config()
