@@ -63,3 +63,58 @@ def get_metrics_results(topk_results, metrics, targets=None):
         else:
             raise NotImplementedError
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Tensor form of the same metrics: the evaluation loop of tasks/test_SMB_decoder.py:196-283
+# detokenises K strings per user, compares strings on the host and pickles hit lists between ranks; here the decoded
+# code tuples are compared as integers on the device they were decoded on, and only the metric sums leave it.
+# ----------------------------------------------------------------------------------------------------------------------
+def pack_targets(targets, width, device=None):
+    """Per-user lists of target tuples -> (padded [B, T_max, width] int64 tensor filled with -1, counts [B])."""
+    import torch
+    B = len(targets)
+    t_max = max(1, max(len(t) for t in targets))
+    out = torch.full((B, t_max, width), -1, dtype=torch.int64)
+    cnt = torch.zeros(B, dtype=torch.int64)
+    for b, tl in enumerate(targets):
+        uniq = sorted(set(tuple(int(x) for x in t) for t in tl))      # the reference compares against set(targets)
+        cnt[b] = len(uniq)
+        for j, t in enumerate(uniq):
+            out[b, j] = torch.tensor(t, dtype=torch.int64)
+    return out.to(device), cnt.to(device)
+
+
+def topk_hits(generated, targets):
+    """generated [B, K, S] int64 (best first), targets [B, T, S] (-1 padded) -> hits [B, K] (1 where the beam's tuple is
+    one of the user's targets) — get_topk_results on id tuples."""
+    eq = (generated[:, :, None, :] == targets[:, None, :, :]).all(-1)          # [B, K, T]
+    return eq.any(-1).to(generated.dtype)
+
+
+def metric_sums(hits, n_targets, metrics):
+    """hits [B, K], n_targets [B] -> {metric: SUM over users} as device scalars; same definitions as hit_k / recall_k /
+    ndcg_k above (multi-target: recall = min(hits, nT) / nT; ndcg stops counting once every target is found and is
+    normalised by the ideal DCG of min(k, nT) hits)."""
+    import torch
+    out = {}
+    B, K = hits.shape
+    disc = 1.0 / torch.log2(torch.arange(K, device=hits.device, dtype=torch.float64) + 2.0)
+    nt = n_targets.clamp(min=1)
+    for m in metrics:
+        kind, k = m.lower().split("@")[0], int(m.split("@")[1])
+        h = hits[:, :k].to(torch.float64)
+        if kind.startswith("hit"):
+            out[m] = (h.sum(1) > 0).to(torch.float64).sum()
+        elif kind.startswith("recall"):
+            out[m] = (torch.minimum(h.sum(1), nt.to(torch.float64)) / nt).sum()
+        elif kind.startswith("ndcg"):
+            found_before = torch.cumsum(h, 1) - h                               # hits strictly before rank j
+            live = found_before < nt.unsqueeze(1)                               # the reference breaks once all are found
+            dcg = (h * live * disc[:k]).sum(1)
+            ideal_len = torch.minimum(nt, torch.tensor(k, device=hits.device))
+            ideal = torch.cumsum(disc[:k], 0)[(ideal_len - 1).clamp(min=0)]
+            out[m] = (dcg / ideal).sum()
+        else:
+            raise NotImplementedError(m)
+    return out

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from . import modeling
 from . import synthetic as syn
 from .distributed import reduce_metric_sums, shard_range, world_info
-from .ranking import get_metrics_results, get_topk_results
+from .ranking import metric_sums, pack_targets, topk_hits
 from .trie import flat_from_array, prefix_allowed_tokens_fn_by_last_token
 
 BACKBONES = {
@@ -182,15 +182,16 @@ def test_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, d
             out = model.generate(**{k: v.to(dev) for k, v in batch.items()}, max_new_tokens=syn.TOKENS_PER_ITEM - 1,
                                  prefix_allowed_tokens_fn=fn, num_beams=num_beams, num_return_sequences=num_beams,
                                  output_scores=True, return_dict_in_generate=True, early_stopping=True)
-            gen = out.sequences[:, -(syn.TOKENS_PER_ITEM - 1):].cpu().tolist()
-            pred = ["".join(f"<{t}>" for t in row) for row in gen]          # detokenised form: one tag per code token
-            tgt = [["".join(f"<{t}>" for t in tup) for tup in tl] for tl in targets]
-            hits = get_topk_results(pred, out.sequences_scores.cpu().tolist(), tgt, num_beams)
-            res = get_metrics_results(hits, metric_list, tgt)
+            # hit matching and metric sums on the device, on the code-id tuples themselves (ranking.py: the tensor form is
+            # checked against the string functions of the reference in tests/test_ranking_device_cpu.py)
+            S = syn.TOKENS_PER_ITEM - 1
+            gen = out.sequences[:, -S:].view(n, num_beams, S)
+            tt, cnt = pack_targets(targets, S, device=dev)
+            res = metric_sums(topk_hits(gen, tt), cnt, metric_list)
             for m in metric_list:
-                sums[m] += res[m]
+                sums[m] = sums[m] + res[m]
             count += n
-        means, total = reduce_metric_sums(sums, count, device=dev)
+        means, total = reduce_metric_sums({m: float(v) for m, v in sums.items()}, count, device=dev)   # one sync
         means["eval_type"] = f"Behavior {beh_name}"
         results.append(means)
         for m in metric_list:
