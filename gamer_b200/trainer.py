@@ -141,6 +141,7 @@ class NativeTrainer:
         s_inv = inv_norm.clone()
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()     # hand the eager run's cached activations back: the graph gets its own pool
         with torch.cuda.graph(g):
             loss = self._run_micro(static, s_inv, None)
         if len(self.graphs) >= self.max_graphs:
