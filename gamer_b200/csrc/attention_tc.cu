@@ -815,12 +815,24 @@ struct BwdParams {
 
 template <int KIND>
 __device__ __forceinline__ void bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask) {
-    // (sequence, kv head)-major: the k_tiles items of one group run at the same time on neighbouring CTAs, so their Q / dO
-    // tiles and dQ accumulator tiles are shared through L2 instead of being re-fetched from HBM once per key tile.  The key
-    // tile is rotated by the group index: with a grid stride that is a multiple of k_tiles a CTA would otherwise always draw
-    // the same (heaviest or lightest) key tile.
-    const int grp = w / p.k_tiles;
-    kt = (w % p.k_tiles + grp) % p.k_tiles;
+    // Work order.  A "group" = (sequence, kv head); its k_tiles items share Q / dO tiles and dQ accumulator tiles.
+    //  * full rounds: groups are dealt one per CTA and a CTA walks ITS group's key tiles 0..k_tiles-1 back to back (w
+    //    advances by gridDim.x between its items): every CTA carries the same load, and the group's tiles stay in L2;
+    //  * the last (n_groups mod gridDim.x) groups are dealt key-tile-major over all CTAs, heaviest key tile first (tile 0
+    //    meets the most query tiles), so the tail of the launch is made of the light items.
+    const int grid = (int)gridDim.x;
+    const int n_groups = p.B * p.n_kv;
+    const int full = (n_groups / grid) * grid;
+    int grp;
+    if (w < full * p.k_tiles) {
+        const int r = w % (grid * p.k_tiles);
+        kt = r / grid;
+        grp = (w / (grid * p.k_tiles)) * grid + r % grid;
+    } else {
+        const int wr = w - full * p.k_tiles, rem = n_groups - full;
+        kt = wr / rem;
+        grp = full + wr % rem;
+    }
     b = grp / p.n_kv;
     g = grp % p.n_kv;
     const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
