@@ -29,20 +29,34 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, long long ld_gu, 
     const int vshift = pow2_shift(vec_per_row);
     dp = drop_resolve(dp);
     const long long total = R * vec_per_row;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r;
-        int c;
-        split_index(i, vec_per_row, vshift, r, c);
-        float g[8], u[8], o[8];
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + c), g);
-        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(gu + r * ld_gu + I + c), u);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // two vectors per iteration: their four 16-byte loads are issued before any arithmetic
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        long long r[2];
+        int c[2];
+        bf16x8 gv[2], uv[2];
+        int mrow[2];
+        bool ok[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = g[k] * sigmoidf_(g[k]) * u[k];
-        if (dp.thresh) {
-            const long long mr = row_ids ? (long long)row_ids[r] : r;
-            if (mr >= 0) drop_apply8(dp, (uint32_t)mr, (uint32_t)(c >> 3), o);
+        for (int t = 0; t < 2; ++t) {
+            const long long i = i0 + t * stride;
+            ok[t] = i < total;
+            split_index(ok[t] ? i : 0, vec_per_row, vshift, r[t], c[t]);
+            gv[t] = *reinterpret_cast<const bf16x8*>(gu + r[t] * ld_gu + c[t]);
+            uv[t] = *reinterpret_cast<const bf16x8*>(gu + r[t] * ld_gu + I + c[t]);
+            mrow[t] = (dp.thresh && row_ids) ? row_ids[r[t]] : (int)r[t];
         }
-        *reinterpret_cast<bf16x8*>(act + r * ld_act + c) = float_to_bf16x8(o);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!ok[t]) continue;
+            float g[8], u[8], o[8];
+            bf16x8_to_float(gv[t], g);
+            bf16x8_to_float(uv[t], u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = g[k] * sigmoidf_(g[k]) * u[k];
+            if (dp.thresh && mrow[t] >= 0) drop_apply8(dp, (uint32_t)mrow[t], (uint32_t)(c[t] >> 3), o);
+            *reinterpret_cast<bf16x8*>(act + r[t] * ld_act + c[t]) = float_to_bf16x8(o);
+        }
     }
 }
 

@@ -227,12 +227,24 @@ class FlatPack(Pack):
             d["w_d_t"].view(E_, d["w_d"].shape[1], -1).copy_(d["w_d"].view(E_, -1, d["w_d"].shape[1]).transpose(1, 2))
 
 
+_ROPE_CACHE: dict = {}
+
+
 def rope_tables(arch: Arch, n_pos: int, device):
-    """cos/sin [n_pos, head_dim/2] fp32, computed as Qwen3RotaryEmbedding does (fp32 outer product, then cos/sin)."""
+    """cos/sin [n_pos, head_dim/2] fp32, computed as Qwen3RotaryEmbedding does (fp32 outer product, then cos/sin).
+    Cached per (head_dim, theta, n_pos, device): the tables are constants, and a cached tensor keeps its address across
+    CUDA-graph replays."""
+    key = (arch.head_dim, arch.theta, n_pos, str(device))
+    hit = _ROPE_CACHE.get(key)
+    if hit is not None:
+        return hit
     d = arch.head_dim
     inv = 1.0 / (arch.theta ** (torch.arange(0, d, 2, dtype=torch.float32, device=device) / d))
     f = torch.arange(n_pos, dtype=torch.float32, device=device).unsqueeze(-1) * inv
-    return f.cos().contiguous(), f.sin().contiguous()
+    tabs = (f.cos().contiguous(), f.sin().contiguous())
+    if not torch.cuda.is_current_stream_capturing():
+        _ROPE_CACHE[key] = tabs      # never evicted: captured graphs may hold the address (≈ 130 KB per sequence length)
+    return tabs
 
 
 def behaviour_lut(arch: Arch, device):
