@@ -14,24 +14,24 @@ import sys
 
 
 def parse_global_args(parser):
-    parser.add_argument("--seed", type=int, default=42, help="Random seed")
-    parser.add_argument("--backbone", type=str, default="TIGER", help="The backbone model to use")
-    parser.add_argument("--base_model", type=str, default="./config/s2s-models/TIGER", help="Basic model path")
-    parser.add_argument("--output_dir", type=str, default="./checkpoint/decoder", help="The output directory")
+    parser.add_argument("--seed", type=int, default=42)
+    parser.add_argument("--backbone", type=str, default="TIGER")
+    parser.add_argument("--base_model", type=str, default="./config/s2s-models/TIGER")
+    parser.add_argument("--output_dir", type=str, default="./checkpoint/decoder")
     return parser
 
 
 def parse_dataset_args(parser):
-    parser.add_argument("--data_path", type=str, default="./data", help="data directory")
-    parser.add_argument("--tasks", type=str, default="seqrec", help="Downstream tasks, separate by comma")
-    parser.add_argument("--dataset", type=str, default="Instruments", help="Dataset name")
-    parser.add_argument("--index_file", type=str, default=".index.json", help="the item indices file")
-    parser.add_argument("--max_his_len", type=int, default=20, help="the max number of items in history sequence")
+    parser.add_argument("--data_path", type=str, default="./data")
+    parser.add_argument("--tasks", type=str, default="seqrec")
+    parser.add_argument("--dataset", type=str, default="Instruments")
+    parser.add_argument("--index_file", type=str, default=".index.json")
+    parser.add_argument("--max_his_len", type=int, default=20)
     return parser
 
 
 def add_train(sub):
-    p = sub.add_parser("train_SMB_decoder", help="Train a decoder for session-wise multi-behavior recommendation.")
+    p = sub.add_parser("train_SMB_decoder")
     parse_dataset_args(parse_global_args(p))
     p.add_argument("--optim", type=str, default="adamw_torch")
     p.add_argument("--epochs", type=int, default=200)
@@ -57,16 +57,16 @@ def add_train(sub):
 
 
 def add_test(sub):
-    p = sub.add_parser("test_SMB_decoder", help="Test a SMB decoder for SeqRec.")
+    p = sub.add_parser("test_SMB_decoder")
     parse_dataset_args(parse_global_args(p))
-    p.add_argument("--ckpt_path", type=str, default="./checkpoint", help="The checkpoint path")
-    p.add_argument("--results_file", type=str, default="./results/test.json", help="result output path")
+    p.add_argument("--ckpt_path", type=str, default="./checkpoint")
+    p.add_argument("--results_file", type=str, default="./results/test.json")
     p.add_argument("--test_batch_size", type=int, default=16)
     p.add_argument("--num_beams", type=int, default=20)
     p.add_argument("--metrics", type=str, default="hit@1,hit@5,hit@10,recall@1,recall@5,recall@10,ndcg@5,ndcg@10")
     p.add_argument("--test_task", type=str, default="SeqRec")
-    p.add_argument("--behaviors", type=str, nargs="+", default=None, help="The behavior list.")
-    p.add_argument("--valid_loss", action="store_true", help="Whether to calculate valid loss instead of testing.")
+    p.add_argument("--behaviors", type=str, nargs="+", default=None)
+    p.add_argument("--valid_loss", action="store_true")
     p.add_argument("--synthetic_users", type=int, default=1024, help="(gamer_b200) synthetic test users per behaviour")
     p.add_argument("--synthetic_items", type=int, default=50_000, help="(gamer_b200) synthetic catalogue size")
 
