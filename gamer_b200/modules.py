@@ -22,35 +22,34 @@ _ACT = {"gelu": F.gelu, "relu": F.relu, "swish": F.silu, "tanh": torch.tanh, "si
 
 class MultiHeadAttention(nn.Module):
     """Post-LN self attention: LayerNorm(x + dropout(dense(softmax(QK^T / sqrt(d) + mask) V)))."""
+    _PROJ = ("query", "key", "value")
 
     def __init__(self, embed_dim: int, num_heads: int, dropout: float, layer_norm_eps: float):
         super().__init__()
-        if embed_dim % num_heads != 0:
+        head, rest = divmod(embed_dim, num_heads)
+        if rest:
             raise ValueError("The hidden size (%d) is not a multiple of the number of attention heads (%d)"
                              % (embed_dim, num_heads))
-        self.num_attention_heads = num_heads
-        self.attention_head_size = embed_dim // num_heads
-        self.all_head_size = self.num_attention_heads * self.attention_head_size
-        self.query = nn.Linear(embed_dim, self.all_head_size)
-        self.key = nn.Linear(embed_dim, self.all_head_size)
-        self.value = nn.Linear(embed_dim, self.all_head_size)
+        self.num_attention_heads, self.attention_head_size, self.all_head_size = num_heads, head, num_heads * head
+        for name in self._PROJ:                                   # query / key / value: the reference's parameter names
+            setattr(self, name, nn.Linear(embed_dim, self.all_head_size))
         self.attn_dropout = nn.Dropout(dropout)
         self.dense = nn.Linear(embed_dim, embed_dim)
         self.LayerNorm = nn.LayerNorm(embed_dim, eps=layer_norm_eps)
         self.out_dropout = nn.Dropout(dropout)
 
     def transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
-        return x.view(*x.shape[:-1], self.num_attention_heads, self.attention_head_size).permute(0, 2, 1, 3)
+        """[B, L, heads * d] -> [B, heads, L, d]"""
+        B, L, _ = x.shape
+        return x.view(B, L, self.num_attention_heads, self.attention_head_size).transpose(1, 2)
 
     def forward(self, input_tensor: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
-        q = self.transpose_for_scores(self.query(input_tensor))
-        k = self.transpose_for_scores(self.key(input_tensor))
-        v = self.transpose_for_scores(self.value(input_tensor))
-        mask = None if attention_mask is None else attention_mask.to(q.dtype)
-        ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
-                                             dropout_p=self.attn_dropout.p if self.training else 0.0)
-        ctx = ctx.permute(0, 2, 1, 3).reshape(*input_tensor.shape[:-1], self.all_head_size)
-        return self.LayerNorm(self.out_dropout(self.dense(ctx)) + input_tensor)
+        q, k, v = (self.transpose_for_scores(getattr(self, name)(input_tensor)) for name in self._PROJ)
+        bias = attention_mask if attention_mask is None else attention_mask.to(q.dtype)     # additive, broadcastable
+        p_drop = self.attn_dropout.p if self.training else 0.0
+        mixed = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=p_drop)   # scale = d ** -0.5
+        mixed = mixed.transpose(1, 2).flatten(2)
+        return self.LayerNorm(input_tensor + self.out_dropout(self.dense(mixed)))
 
 
 class FeedForward(nn.Module):
@@ -61,22 +60,19 @@ class FeedForward(nn.Module):
     def __init__(self, d_model: int, dim_feedforward: int, dropout: float,
                  activation: str | Callable[[torch.Tensor], torch.Tensor], layer_norm_eps: float, residual: bool = True):
         super().__init__()
-        self.dense_1 = nn.Linear(d_model, dim_feedforward)
-        self.intermediate_act_fn = _ACT[activation] if isinstance(activation, str) else activation
-        self.dense_2 = nn.Linear(dim_feedforward, d_model)
+        self.dense_1, self.dense_2 = nn.Linear(d_model, dim_feedforward), nn.Linear(dim_feedforward, d_model)
+        self.intermediate_act_fn = self.get_hidden_act(activation) if isinstance(activation, str) else activation
         self.residual = residual
-        if self.residual:
-            self.LayerNorm = nn.LayerNorm(d_model, eps=layer_norm_eps)
-            self.dropout = nn.Dropout(dropout)
+        if residual:
+            self.LayerNorm, self.dropout = nn.LayerNorm(d_model, eps=layer_norm_eps), nn.Dropout(dropout)
 
-    def get_hidden_act(self, act: str):
+    @staticmethod
+    def get_hidden_act(act: str):
         return _ACT[act]
 
     def forward(self, input_tensor: torch.Tensor) -> torch.Tensor:
-        hidden_states = self.dense_2(self.intermediate_act_fn(self.dense_1(input_tensor)))
-        if not self.residual:
-            hidden_states = self.LayerNorm(self.dropout(hidden_states) + input_tensor)
-        return hidden_states
+        y = self.dense_2(self.intermediate_act_fn(self.dense_1(input_tensor)))
+        return y if self.residual else self.LayerNorm(input_tensor + self.dropout(y))
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -91,11 +87,13 @@ class TransformerEncoderLayer(nn.Module):
 
 
 class TransformerEncoder(nn.Module):
+    """`num_layers` independent copies of `encoder_layer`, applied in order with the same mask."""
+
     def __init__(self, encoder_layer: nn.Module, num_layers: int):
         super().__init__()
-        self.layer = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.layer = nn.ModuleList(copy.deepcopy(encoder_layer) for _ in range(num_layers))
 
     def forward(self, hidden_states, attention_mask: torch.Tensor, **kwargs):
-        for layer_module in self.layer:
-            hidden_states = layer_module(hidden_states, attention_mask, **kwargs)
+        for block in self.layer:
+            hidden_states = block(hidden_states, attention_mask, **kwargs)
         return hidden_states
