@@ -37,6 +37,20 @@ void gamer_set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: a call site keeps one flag per device ordinal (a process may drive several GPUs)
+struct PerDeviceOnce {
+    unsigned long long value[64] = {};
+    // true when `want` exceeds what this call site has configured on the current device (and records it)
+    bool need(unsigned long long want = 1) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        unsigned long long& v = value[dev & 63];
+        if (want <= v) return false;
+        v = want;
+        return true;
+    }
+};
+
 // mask kinds (include/gamer_b200.h: GAMER_MASK_*)
 enum { MASK_CAUSAL = 0, MASK_MULTI_CROSS = 1, MASK_SESSION = 2, MASK_SESSION_CROSS = 3 };
 

@@ -369,11 +369,9 @@ extern "C" int gamer_beam_step(const float* logits, long long ld, int vocab, int
     const int cap = beams * max_children;                      // every beam's node has <= max_children children
     const size_t smem = (size_t)cap * (sizeof(float) + sizeof(int) + sizeof(short)) + 16;
     GAMER_REQUIRE(smem <= 200 * 1024, "beams * max_children = %d candidates do not fit in shared memory", cap);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceOnce configured;
+    if (configured.need(smem))
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     beam_step_kernel<<<n_users, 256, smem, stream>>>(logits, ld, vocab, beams, run_score, node, child_start, child_tok,
                                                      child_node, new_score, new_parent, new_tok, new_node, err, cap);
     GAMER_LAUNCH_CHECK();

@@ -648,11 +648,9 @@ int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
                    const GemmParams& p, cudaStream_t stream) {
     using S = GemmCfg<OUT_F32, STAGED, BN>;
     auto kern = gemm_tn_kernel<OUT_F32, STAGED, BN>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need())
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        configured = true;
-    }
     const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
@@ -741,11 +739,9 @@ extern "C" int gamer_gemm_bf16_wgrad(const void* dY, long long ldy, const void* 
         GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (dW) failed with %d (N_out=%d K_in=%d groups=%d)", (int)r, N_out,
                       K_in, n_groups);
     }
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need())
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_TOTAL));
-        configured = true;
-    }
     // chunk the token rows so that (groups x tiles x chunks) fills one wave of CTAs as evenly as possible
     const int tiles = n_groups * p.n_i * p.n_j;
     const int chunks_per_group = tiles >= num_sms() ? 1 : num_sms() / tiles;

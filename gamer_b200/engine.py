@@ -328,15 +328,15 @@ def _attention_fwd(arch, meta, x, norm_w, w_qkv, qn, kn, w_o, kind, tabs, act_id
     qe, ke, ve = embs if embs is not None else (None, None, None)
     rot = K.qk_norm_rope_fwd(raw, meta.L, arch.n_q, arch.n_kv, arch.head_dim, tabs[0], tabs[1], qn, kn, arch.eps,
                              pos_ids=meta.rope_pos, q_emb=qe, k_emb=ke, v_emb=ve, act_idx=act_idx)
-    o, lse, vmean = K.attn_fwd(rot, meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P, meta.am, meta.act,
-                               meta.sess, arch.head_dim ** -0.5, drop=drop_p)
+    o, lse, vmean, keep = K.attn_fwd(rot, meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P, meta.am,
+                                     meta.act, meta.sess, arch.head_dim ** -0.5, drop=drop_p)
     if gated:
         y = K.gemm_tn(o, w_o, arch.hidden)
         x_out = K.gate_residual_fwd(x, y, raw[:, arch.qkv_w:], drop=drop_out)
     else:
         y = None
         x_out = K.gemm_tn(o, w_o, arch.hidden, resid=x, drop=drop_out)
-    return x_out, dict(x=x, rstd=rstd, h=h, raw=raw, rot=rot, o=o, lse=lse, y=y, vmean=vmean)
+    return x_out, dict(x=x, rstd=rstd, h=h, raw=raw, rot=rot, o=o, lse=lse, y=y, vmean=vmean, keep=keep)
 
 
 def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save: bool, kv_sink: list | None = None,
@@ -443,7 +443,7 @@ def _attention_bwd(arch, meta, s, dx_out, norm_w, w_qkv_t, qn, kn, w_o_t, kind, 
     K.gemm_wgrad(dy, s["o"], arch.hidden, arch.q_w, G[names["o"]].view(1, arch.hidden, arch.q_w))
     drot = torch.empty(M, arch.qkv_w, dtype=BF16, device=dev)
     K.attn_bwd(s["rot"], s["o"], d_o, s["lse"], meta.B, meta.L, arch.n_q, arch.n_kv, arch.head_dim, kind, arch.P,
-               meta.am, meta.act, meta.sess, arch.head_dim ** -0.5, drot, drop=drop_p)
+               meta.am, meta.act, meta.sess, arch.head_dim ** -0.5, drot, drop=drop_p, keep=s["keep"])
     qe, ke, ve = embs if embs is not None else (None, None, None)
     K.qk_norm_rope_bwd(s["raw"], drot, draw, meta.L, arch.n_q, arch.n_kv, arch.head_dim, tabs[0], tabs[1], qn, kn,
                        arch.eps, G[names["qn"]], G[names["kn"]], pos_ids=meta.rope_pos, q_emb=qe, k_emb=ke, v_emb=ve,

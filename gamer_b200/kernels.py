@@ -163,22 +163,26 @@ def ref_gemm_tn(a, b, N, K):
 # ------------------------------------------------------------------------------------------------ K6
 def attn_fwd(qkv, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, drop=None):
     """qkv bf16 [B*L, ld]: q cols [0, n_q*hd), k next n_kv*hd, v next n_kv*hd.
-    -> (o [B*L, n_q*hd], lse [B,n_q,L], vmean fp32 [B, n_kv, hd] = mean of all L value rows)."""
+    -> (o [B*L, n_q*hd], lse [B,n_q,L], vmean fp32 [B, n_kv, hd] = mean of all L value rows, keep words | None).
+    `keep` (dropout on) holds the keep flags the backward of this call site reads back."""
     dev = qkv.device
     ws = torch.empty(lib().gamer_attn_workspace_bytes(B, L, n_q, n_kv), dtype=torch.uint8, device=dev)
     o = torch.empty(B * L, n_q * hd, dtype=BF16, device=dev)
     lse = torch.empty(B, n_q, L, dtype=torch.float32, device=dev)
+    keep = None
+    if drop is not None and drop.p > 0:
+        keep = torch.empty(lib().gamer_attn_keep_bytes(B, L, n_q) // 4, dtype=torch.int32, device=dev)
     esz = 2
     q = qkv.data_ptr()
     k = q + n_q * hd * esz
     v = k + n_kv * hd * esz
     call("gamer_attn_fwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
-         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _drop(drop), _stream(),
+         float(scale), ptr(ws), ptr(o), o.stride(0), ptr(lse), _drop(drop), ptr(keep), _stream(),
          work=(4 * hd * n_q * B * L * (L + 1) // 2, B * L * (2 * n_q + 2 * n_kv) * hd * 2))   # causal pair count (§8d)
-    return o, lse, ws[: B * n_kv * hd * 4].view(torch.float32).view(B, n_kv, hd)
+    return o, lse, ws[: B * n_kv * hd * 4].view(torch.float32).view(B, n_kv, hd), keep
 
 
-def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv, drop=None):
+def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scale, dqkv, drop=None, keep=None):
     dev = qkv.device
     ws = torch.empty(lib().gamer_attn_bwd_workspace_bytes(B, L, n_q), dtype=torch.uint8, device=dev)
     esz = 2
@@ -190,7 +194,7 @@ def attn_bwd(qkv, o, d_o, lse, B, L, n_q, n_kv, hd, kind, P, am, act, sess, scal
     dv = dk + n_kv * hd * esz
     call("gamer_attn_bwd", q, k, v, qkv.stride(0), B, L, n_q, n_kv, hd, kind, P, ptr(am), ptr(act), ptr(sess),
          float(scale), ptr(o), ptr(d_o), o.stride(0), ptr(lse), ptr(ws), dq, dk, dv, dqkv.stride(0), _drop(drop),
-         _stream(),
+         ptr(keep), _stream(),
          work=(10 * hd * n_q * B * L * (L + 1) // 2, B * L * (4 * n_q + 4 * n_kv) * hd * 2))
     return dqkv
 

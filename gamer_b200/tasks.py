@@ -76,6 +76,24 @@ def _batches(cat, n_rows, batch, max_his_len, seed):
     return out
 
 
+_PAD_VALUE = {"input_ids": syn.PAD, "attention_mask": 0, "labels": -100, "actions": 100, "session_ids": 0,
+              "extended_session_ids": 0}
+
+
+def _pad_to_common_length(batch, dev):
+    """Every rank must replay / capture the same micro-batch shape and issue the same collectives: right-pad this rank's
+    ragged batch to the longest row of any rank (one MAX all-reduce of a scalar per step)."""
+    L = torch.tensor([batch["input_ids"].shape[1]], device=dev)
+    dist.all_reduce(L, op=dist.ReduceOp.MAX)
+    L = int(L)
+    out = {}
+    for k, v in batch.items():
+        if v.shape[1] < L:
+            v = torch.nn.functional.pad(v, (0, L - v.shape[1]), value=_PAD_VALUE[k])
+        out[k] = v
+    return out
+
+
 @torch.no_grad()
 def _valid_loss(model, batches, dev):
     """`--valid_loss` / per-epoch evaluation: mean of the per-batch losses (test_SMB_decoder.py:306-322)."""
@@ -108,10 +126,12 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
     cat = syn.make_catalogue(synthetic_items, 1234)
-    lo, hi = shard_range(synthetic_users, rank, world)
+    # equal rows per rank (the remainder of an uneven split is dropped, as DistributedSampler(drop_last) would): every
+    # rank then runs the same number of optimizer steps with the same batch sizes — and so the same NCCL sequence
+    n_rows = synthetic_users // world
     step_rows = per_device_batch_size * gradient_accumulation_steps
-    train = _batches(cat, hi - lo, step_rows, max_his_len, seed=10_000 * (rank + 1))
-    valid = _batches(cat, max(per_device_batch_size, (hi - lo) // 8), per_device_batch_size, max_his_len, seed=777_000 + rank)
+    train = _batches(cat, n_rows, step_rows, max_his_len, seed=10_000 * (rank + 1))
+    valid = _batches(cat, max(per_device_batch_size, n_rows // 8), per_device_batch_size, max_his_len, seed=777_000 + rank)
     total_steps = epochs * len(train)
     trainer = NativeTrainer(model, lr=learning_rate, weight_decay=weight_decay, max_grad_norm=1.0,
                             warmup_steps=int(math.ceil(warmup_ratio * total_steps)), total_steps=total_steps)
@@ -123,7 +143,10 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
     for epoch in range(epochs):
         t0, seen = time.time(), 0
         for b in train:
-            loss = trainer.step({k: v.to(dev, non_blocking=True) for k, v in b.items()}, micro_batch=per_device_batch_size)
+            b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+            if world > 1:
+                b = _pad_to_common_length(b, dev)
+            loss = trainer.step(b, micro_batch=per_device_batch_size)
             step += 1
             seen += b["input_ids"].shape[0]
             if step % logging_step == 0:

@@ -19,6 +19,7 @@ loop underneath it, restated B200-first:
 from __future__ import annotations
 
 import math
+import re
 
 import torch
 import torch.distributed as dist
@@ -32,12 +33,22 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Name patterns exempt from weight decay.  "hf-4.51": the release the reference pins (bias / layernorm / rmsnorm in the
+# qualified name: input_layernorm and post_attention_layernorm are exempt, q_norm / k_norm / model.norm are decayed);
+# "hf-5": the list of the transformers 5.x installed here (every *norm weight exempt).
+DECAY_EXEMPT = {
+    "hf-4.51": (r"bias", r"layernorm", r"rmsnorm"),
+    "hf-5": (r"bias", r"layernorm", r"rmsnorm", r"(?:^|\.)norm(?:$|\.)", r"_norm(?:$|\.)"),
+}
+HP_SLOTS = 8          # pinned staging slots for the per-step scalars (see optimizer_step)
+
+
 class NativeTrainer:
     BATCH_KEYS = ("input_ids", "attention_mask", "labels", "actions", "session_ids", "extended_session_ids")
 
     def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
                  warmup_steps=0, total_steps=None, process_group=None, min_lr_ratio=0.0, use_cuda_graphs=True,
-                 max_graphs=4):
+                 max_graphs=4, decay_rule="hf-4.51"):
         self.model = model
         self.arch = model.arch
         dev = next(model.parameters()).device
@@ -58,12 +69,13 @@ class NativeTrainer:
             for k, p in params.items():
                 views[k].copy_(p.data)
                 p.data = views[k]
-        # HF Trainer: no weight decay on norm weights (get_decay_parameter_names); embeddings and linears decay
+        # HF Trainer.get_decay_parameter_names: weight decay skips parameters whose qualified name matches a pattern
+        # list that changed between releases (DECAY_EXEMPT); the reference pins transformers 4.51
         mask = torch.zeros(n, dtype=torch.uint8, device=dev)
         mviews = E.unfuse_grads(a, E.flat_views(a, mask))
+        exempt = [re.compile(pat) for pat in DECAY_EXEMPT[decay_rule]]
         for k in params:
-            leaf = k.split(".")[-2]
-            if not ("norm" in leaf or "layernorm" in leaf):
+            if not any(pat.search(k.lower()) for pat in exempt):
                 mviews[k].fill_(1)
         self.decay_mask = mask
         self.G = E.grad_buffers(a, dev, self.flat_g)
@@ -74,7 +86,8 @@ class NativeTrainer:
         self.pg = process_group
         self.reducer = BucketReducer(self.flat_g, self.ranges, process_group)
         self.world = self.reducer.world
-        self.hp_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.hp_host = torch.zeros(HP_SLOTS, 4, dtype=torch.float32).pin_memory()
+        self.hp_events = [None] * HP_SLOTS
         self.hp = torch.zeros(4, dtype=torch.float32, device=dev)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lut = E.behaviour_lut(a, dev)
@@ -160,7 +173,12 @@ class NativeTrainer:
         if entry is None:
             self.seen[key] = self.seen.get(key, 0) + 1
             if self.seen[key] < 2:                 # first occurrence of a shape: eager (also the kernels' warm-up)
-                return self._run_micro(batch, inv_norm, self._bucket_hook if last_micro else None)
+                # same collective as the replays (one flat all-reduce), so ranks whose graph caches differ — ragged
+                # batches give every rank its own shape history — still issue identical NCCL sequences
+                loss = self._run_micro(batch, inv_norm, None)
+                if last_micro:
+                    self.reducer.launch_flat()
+                return loss
             entry = self._capture(key, batch, inv_norm)      # capture records, it does not execute
         g, static, s_inv, loss = entry
         for k, v in static.items():
@@ -191,12 +209,23 @@ class NativeTrainer:
     def optimizer_step(self):
         """clip + AdamW + bf16 operand refresh.  Step-dependent scalars (lr, bias corrections) travel through a small
         device tensor, so with CUDA graphs the ~70 launches of this method are captured once and replayed."""
+        # HF LambdaLR: update k (1-based) runs with lambda(k-1); Adam's bias corrections use t = k.
+        lr = self.current_lr()
         self.step_idx += 1
         t = self.step_idx
-        self.hp_host[0] = self.current_lr()
-        self.hp_host[1] = 1.0 - self.betas[0] ** t
-        self.hp_host[2] = 1.0 - self.betas[1] ** t
-        self.hp.copy_(self.hp_host, non_blocking=True)
+        # The host runs ahead of the device (graph replays are asynchronous), so every step stages its scalars in its own
+        # pinned slot; a slot is rewritten only after the H2D copy that last read it has completed.
+        slot = t % HP_SLOTS
+        if self.hp_events[slot] is not None:
+            self.hp_events[slot].synchronize()
+        row = self.hp_host[slot]
+        row[0] = lr
+        row[1] = 1.0 - self.betas[0] ** t
+        row[2] = 1.0 - self.betas[1] ** t
+        self.hp.copy_(row, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.hp_events[slot] = ev
         if not self.use_cuda_graphs:
             self._optimizer_kernels()
         elif self.opt_graph is None:

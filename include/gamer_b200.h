@@ -104,17 +104,20 @@ int gamer_ref_gemm_tn(const void* A, long long lda, const void* B, long long ldb
 
 /* ---- K6: masked attention (replaces mask materialisation + SDPA, Qwen3Multi/model.py:123-143,573-741) ---------- */
 long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv);
-/* debug hook (tools/attn_trace.py): record an in-kernel timeline of CTA 0 of the next forward launches; buf = NULL disables */
-int gamer_attn_set_trace(void* buf, int cap);
+/* Attention-probability dropout (SDPA dropout_p, Qwen3Multi/model.py:139): the forward writes one keep word per (query,
+ * 32 keys) into `keep` (gamer_attn_keep_bytes bytes; may be NULL when drop is NULL or drop->p == 0) and the backward of the
+ * same call site reads it back, instead of regenerating the random stream. */
+long long gamer_attn_keep_bytes(int B, int L, int n_q);
 int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
                    float scale, void* workspace, void* o, long long ld_o, float* lse, const gamer_dropout_t* drop,
-                   gamer_stream_t stream);
+                   void* keep, gamer_stream_t stream);
 long long gamer_attn_bwd_workspace_bytes(int B, int L, int n_q);
 int gamer_attn_bwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
                    float scale, const void* o, const void* d_o, long long ld_o, const float* lse, void* workspace,
-                   void* dq, void* dk, void* dv, long long ld_d, const gamer_dropout_t* drop, gamer_stream_t stream);
+                   void* dq, void* dk, void* dv, long long ld_d, const gamer_dropout_t* drop, const void* keep,
+                   gamer_stream_t stream);
 
 /* ---- elementwise pieces --------------------------------------------------------------------------------------- */
 /* act = dropout(silu(gate) * up) (Qwen3Moe/FFN.py:26).  row_ids (may be NULL = identity) maps a row of the expert-

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY — numpy restatement of the dropout-mask generator of the CUDA path
-(gamer_b200/csrc/common.cuh: philox4x32_7, drop_keep8, drop_attn16, make_drop).
+(gamer_b200/csrc/common.cuh: philox4x32_7, drop_keep8, make_drop; gamer_b200/csrc/attention_tc.cu: keep_word).
 
 The reference draws its dropout masks from torch's generator (nn.Dropout, SDPA dropout_p: Qwen3Multi/model.py:139,177,
 217,235,241; Qwen3Moe/FFN.py:23-26), so masks can never be bit-identical to it; parity with dropout ON is therefore
@@ -61,19 +61,33 @@ def hidden_keep(seed, offset, site, rows, cols, p):
     return torch.from_numpy((vals >= t).reshape(rows, cols)), scale
 
 
-def attn_keep(seed, offset, site, B, n_q, L, p):
-    """-> (keep bool [B, n_q, L, L(keys)], scale).  8 random bits per (query, key); one Philox call per 16 keys."""
+def attn_keep_words(seed, offset, site, B, n_q, L, p):
+    """-> (uint32 [B*n_q, L, ceil(L/32)] keep words, scale): the words the forward kernel stores (attention_tc.cu:
+    keep_word).  Word (bh, i, jw) covers keys [32 jw, 32 jw + 32): two Philox calls give eight random words r0..r7; lane
+    bit c of r_k is bit k of an 8-bit number R_c, and the lane is dropped iff R_c < thresh."""
     t, scale = _thresh(p, 8)
     k0, k1 = _key(seed, offset)
-    nb = (L + 15) // 16
+    nw = (L + 31) // 32
     bh = np.arange(B * n_q, dtype=np.uint64).reshape(B * n_q, 1, 1)
     i = np.arange(L, dtype=np.uint64).reshape(1, L, 1)
-    jb = np.arange(nb, dtype=np.uint64).reshape(1, 1, nb)
-    w = philox4x32(jb, i, bh, site, k0, k1)
-    vals = np.empty((B * n_q, L, nb, 16), dtype=np.uint32)
-    for e in range(16):
-        vals[..., e] = (w[e >> 2] >> np.uint32(8 * (e & 3))) & np.uint32(0xFF)
-    keep = (vals >= t).reshape(B, n_q, L, nb * 16)[..., :L]
+    jw = np.arange(nw, dtype=np.uint64).reshape(1, 1, nw)
+    r = philox4x32(2 * jw, i, bh, site, k0, k1) + philox4x32(2 * jw + 1, i, bh, site, k0, k1)
+    lanes = np.zeros((B * n_q, L, nw, 32), dtype=np.uint32)       # R_c per lane
+    bit = np.arange(32, dtype=np.uint32)
+    for k in range(8):
+        lanes |= ((r[k][..., None] >> bit) & np.uint32(1)) << np.uint32(k)
+    keep_lane = lanes >= t                                           # lane = bit position of the keep word
+    words = (keep_lane.astype(np.uint32) << bit).sum(axis=-1, dtype=np.uint64).astype(np.uint32)
+    return words, scale
+
+
+def attn_keep(seed, offset, site, B, n_q, L, p):
+    """-> (keep bool [B, n_q, L, L(keys)], scale).  Key 32 jw + 4 g + e of a word sits at bit g + 8 e."""
+    words, scale = attn_keep_words(seed, offset, site, B, n_q, L, p)
+    nw = words.shape[-1]
+    c = np.arange(32)
+    bitpos = ((c >> 2) + 8 * (c & 3)).astype(np.uint32)              # key column within the block -> bit
+    keep = ((words[..., None] >> bitpos) & np.uint32(1)).astype(bool).reshape(B, n_q, L, nw * 32)[..., :L]
     return torch.from_numpy(np.ascontiguousarray(keep)), scale
 
 

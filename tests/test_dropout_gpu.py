@@ -107,10 +107,19 @@ def test_attention_dropout_fwd_bwd(kind, L, left_pad):
     d = k.Dropout(SEED, OFFSET, site, 0.2)
     keep, zs = dm.attn_keep(SEED, OFFSET, site, B, nq, L, 0.2)
     zp = keep.float().to(DEV) * zs
-    o, lse, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale, drop=d)
-    o0, lse0, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
+    o, lse, _, kw = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale, drop=d)
+    o0, lse0, _, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
     assert torch.equal(lse, lse0), "lse must not depend on dropout (softmax is normalised before dropping)"
     allow = om.allow_matrix(kind, am, act, sess, 5).to(DEV)
+    # the keep words the forward stored (layout [b*n_q + h][query tile][32-key block][128 rows]) equal the oracle's wherever
+    # a pair is allowed (blocks without an allowed pair are never generated)
+    words, _ = dm.attn_keep_words(SEED, OFFSET, site, B, nq, L, 0.2)
+    qt_n, nw_p = (L + 127) // 128, 4 * ((L + 127) // 128)
+    got = kw.view(B * nq, qt_n, nw_p, 128).permute(0, 1, 3, 2).reshape(B * nq, qt_n * 128, nw_p)[:, :L, :words.shape[-1]]
+    want = torch.from_numpy(words.astype("int64")).to(DEV)
+    blk_any = torch.nn.functional.pad(allow, (0, words.shape[-1] * 32 - L)).view(B, L, -1, 32).any(-1)   # [B, L, nw]
+    blk_any = blk_any[:, None].expand(B, nq, L, -1).reshape(B * nq, L, -1)
+    assert torch.equal((got.long() & 0xffffffff)[blk_any], want[blk_any]), "stored keep words differ from the oracle generator"
     qf = qkv.float().requires_grad_(True)
     q = qf[:, :384].view(B, L, nq, hd).transpose(1, 2)
     kk = qf[:, 384:576].view(B, L, nkv, hd).transpose(1, 2)
@@ -122,7 +131,7 @@ def test_attention_dropout_fwd_bwd(kind, L, left_pad):
     d_o = bf(torch.randn(M, nq * hd, device=DEV))
     ref.backward(d_o.float())
     dqkv = torch.zeros(M, 768, dtype=torch.bfloat16, device=DEV)
-    k.attn_bwd(qkv, o, d_o, lse, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale, dqkv, drop=d)
+    k.attn_bwd(qkv, o, d_o, lse, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale, dqkv, drop=d, keep=kw)
     g = qf.grad
     for name, sl in (("dq", slice(0, 384)), ("dk", slice(384, 576)), ("dv", slice(576, 768))):
         e = rel_err(dqkv[:, sl], g[:, sl])

@@ -351,7 +351,7 @@ def test_attention_fwd_bwd(kind, L, left_pad):
     qkv = bf(torch.randn(M, 768, device=DEV))
     scale = hd ** -0.5
     i32 = lambda t: t.to(torch.int32).to(DEV).contiguous()
-    o, lse, vmean = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
+    o, lse, vmean, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
     allow = om.allow_matrix(kind, am, act, sess, 5).to(DEV)
     qf = qkv.float().requires_grad_(True)
     q = qf[:, :384].view(B, L, nq, hd).transpose(1, 2)
@@ -436,7 +436,7 @@ def test_attention_long_history(kind):
     qkv = bf(torch.randn(M, 768, device=DEV))
     scale = hd ** -0.5
     i32 = lambda t: t.to(torch.int32).to(DEV).contiguous()
-    o, lse, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
+    o, lse, _, _ = k.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, i32(am), i32(act), i32(sess), scale)
     allow = om.allow_matrix(kind, am, act, sess, 5).to(DEV)
     qf = qkv.float().requires_grad_(True)
     q = qf[:, :384].view(B, L, nq, hd).transpose(1, 2)

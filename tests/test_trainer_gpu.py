@@ -25,13 +25,15 @@ def test_native_step_matches_oracle_adamw():
     batch = {k: v.to(DEV) for k, v in g["batch"].items()}
     loss = tr.step(batch, micro_batch=4)            # 6 rows -> micro-batches of 4 + 2, num_items normalisation
     assert abs(loss.item() - g["loss"].item()) <= 5e-3 * max(1.0, abs(g["loss"].item()))
-    # oracle: same batch, same normalisation, clip 1.0, torch AdamW (no decay on norm weights, as HF Trainer)
+    # oracle: same batch, same normalisation, clip 1.0, torch AdamW; decay groups by the transformers 4.51 name rule
+    # (bias / layernorm / rmsnorm exempt; q_norm, k_norm and model.norm are decayed) the reference pins
     spec = spec_from_golden(g, g["temperature"])
     W = weights_from_golden(g, requires_grad=True)
     om.forward(spec, W, **g["batch"])["loss"].backward()
     named = {k: v for k, v in W.items() if k != "lm_head.weight"}
-    decay = [v for k, v in named.items() if "norm" not in k.split(".")[-2]]
-    no_decay = [v for k, v in named.items() if "norm" in k.split(".")[-2]]
+    exempt = lambda k: any(t in k.lower() for t in ("bias", "layernorm", "rmsnorm"))
+    decay = [v for k, v in named.items() if not exempt(k)]
+    no_decay = [v for k, v in named.items() if exempt(k)]
     for v in named.values():
         if v.grad is None:
             v.grad = torch.zeros_like(v)

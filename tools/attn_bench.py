@@ -53,10 +53,10 @@ def main():
         for kind in (0, 1, 2, 3):
             for p in (0.0, 0.2):
                 drop = K.Dropout(1234, 0, 8 + kind, p) if p > 0 else None
-                o, lse, _ = K.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, am, act, sess, hd ** -0.5, drop=drop)
+                o, lse, _, keep = K.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, am, act, sess, hd ** -0.5, drop=drop)
                 ms_f = timed(lambda: K.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, am, act, sess, hd ** -0.5, drop=drop), a.iters)
                 ms_b = timed(lambda: K.attn_bwd(qkv, o, d_o, lse, B, L, nq, nkv, hd, kind, 5, am, act, sess, hd ** -0.5, dqkv,
-                                                drop=drop), a.iters)
+                                                drop=drop, keep=keep), a.iters)
                 flops = 4 * hd * nq * B * L * (L + 1) // 2
                 print(json.dumps({"kind": kind, "L": L, "batch": B, "dropout": p, "fwd_ms": ms_f, "bwd_ms": ms_b,
                                   "fwd_tflops": flops / ms_f / 1e9, "bwd_tflops": 2.5 * flops / ms_b / 1e9,
