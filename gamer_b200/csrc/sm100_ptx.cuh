@@ -15,11 +15,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded spin: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU box.  The loop must stay
-// rolled: every wait site is inlined into long straight-line kernels.
-static __device__ __noinline__ void mbar_timeout() {
-    printf("gamer_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-    __trap();
-}
+// rolled: every wait site is inlined into long straight-line kernels.  No function call on this path: ptxas gives the
+// registers of a setmaxnreg.inc region only to call-free code.
+__device__ __forceinline__ void mbar_timeout() { __trap(); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t done;
     asm volatile(
