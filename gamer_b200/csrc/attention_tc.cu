@@ -41,6 +41,20 @@ constexpr int BT = 128;               // tile edge: queries (and keys in the bac
 constexpr int TILE_BYTES = BT * D * 2;  // 16 KB: one [128 x 64] bf16 SWIZZLE_128B tile
 constexpr int KC_MAX = 0x7fffffff;
 
+// Optional in-kernel timeline (debug hook gamer_attn_set_trace): one thread per role of CTA 0 appends (tag, clock64) pairs.
+struct Trace {
+    long long* buf;
+    int cap;
+};
+__device__ __forceinline__ void trace_pt(const Trace& tr, int role, int& n, int tag) {
+    if (tr.buf != nullptr && n < tr.cap) {
+        tr.buf[(role * tr.cap + n) * 2] = tag;
+        tr.buf[(role * tr.cap + n) * 2 + 1] = clock64();
+        ++n;
+    }
+}
+Trace g_trace = {nullptr, 0};
+
 template <int KIND>
 __host__ __device__ constexpr bool kind_causal() { return KIND == MASK_CAUSAL || KIND == MASK_MULTI_CROSS; }
 template <int KIND>
@@ -138,27 +152,53 @@ __device__ __forceinline__ WarpRange warp_range(int i, int L, int P, int act_i, 
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return umma_desc_sw128(saddr, 16, 1024); }
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) { return umma_desc_sw128(saddr, lbo, 1024); }
 
+// The issuing warps run converged: every lane waits on the barriers and builds the (warp-uniform) descriptors, one elected
+// lane issues the MMAs and the commits.  (A role wrapped in `if (lane == 0)` makes every tcgen05.mma a divergent-code
+// sequence — election loop, vector-to-uniform register moves, descriptor rebuild — of ~190 cycles, and a backward step
+// has 32 of them.)  Descriptors are built once per operand tile; a k-step adds to the 16-byte address field: +2 for 32
+// bytes along a K-major row, +128 for the 2 KB between 16-row groups of an MN-major tile.
 // D[128 x 128] = A[128 x 64] B[128 x 64]^T, both K-major tiles (k = head dim)
-__device__ __forceinline__ void issue_nt_128x128x64(uint32_t d_tmem, uint32_t sa, uint32_t sb) {
+__device__ __forceinline__ void issue_nt_128x128x64(uint32_t d_tmem, uint32_t sa, uint32_t sb, uint64_t* bar0,
+                                                    uint64_t* bar1 = nullptr) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+    const uint64_t da = desc_k(sa), db = desc_k(sb);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, desc_k(sa + k * 32), desc_k(sb + k * 32), idesc, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k != 0);
+        umma_commit(bar0);
+        if (bar1 != nullptr) umma_commit(bar1);
+    }
+    __syncwarp();
 }
 // D[128 x 64] (+)= A[128 x 128] B[128 x 64]: A K-major in two 64-wide halves (16 KB apart), B MN-major [128 k-rows x 64]
-__device__ __forceinline__ void issue_nn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc) {
+__device__ __forceinline__ void issue_nn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc, uint64_t* bar0,
+                                                    uint64_t* bar1 = nullptr, uint64_t* bar2 = nullptr,
+                                                    uint64_t* bar3 = nullptr) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+    const uint64_t da = desc_k(sa), db = desc_mn(sb, TILE_BYTES);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        umma_bf16(d_tmem, desc_k(sa + (k >> 2) * TILE_BYTES + (k & 3) * 32), desc_mn(sb + k * 2048, TILE_BYTES), idesc,
-                  (acc || k != 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)
+            umma_bf16(d_tmem, da + (k >> 2) * (TILE_BYTES / 16) + (k & 3) * 2, db + k * 128, idesc, (acc || k != 0) ? 1u : 0u);
+        umma_commit(bar0);
+        if (bar1 != nullptr) umma_commit(bar1);
+        if (bar2 != nullptr) umma_commit(bar2);
+        if (bar3 != nullptr) umma_commit(bar3);
+    }
+    __syncwarp();
 }
 // D[128 x 64] (+)= A^T B with A stored [128 k-rows x 128 m] (two 64-wide halves, MN-major) and B [128 k-rows x 64] MN-major
-__device__ __forceinline__ void issue_tn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc) {
+__device__ __forceinline__ void issue_tn_128x64x128(uint32_t d_tmem, uint32_t sa, uint32_t sb, bool acc, uint64_t* bar0,
+                                                    uint64_t* bar1 = nullptr) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+    const uint64_t da = desc_mn(sa, TILE_BYTES), db = desc_mn(sb, TILE_BYTES);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        umma_bf16(d_tmem, desc_mn(sa + k * 2048, TILE_BYTES), desc_mn(sb + k * 2048, TILE_BYTES), idesc,
-                  (acc || k != 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k) umma_bf16(d_tmem, da + k * 128, db + k * 128, idesc, (acc || k != 0) ? 1u : 0u);
+        if (bar0 != nullptr) umma_commit(bar0);
+        if (bar1 != nullptr) umma_commit(bar1);
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -238,14 +278,16 @@ __device__ __noinline__ void rescale_o_row64(uint32_t t_o, float alpha) {
 constexpr int S_KT = 64;                                   // keys per tile
 constexpr int S_HALF = S_KT * D * 2;                       // 8 KB: one [64 x 64] bf16 tile
 constexpr int S_CODES = 640;                               // ka[64] | ks[64] | blk[2] int4 (+ pad)
-constexpr int S_KST = 3;                                   // K (+ key codes) stages
+constexpr int S_KST = 4;                                   // K (+ key codes) stages
+constexpr int S_VST = 3;                                   // V stages
 constexpr int S_OFF_Q = 0;                                 // [128 x 64] Q, later the O staging tile
 constexpr int S_OFF_K = TILE_BYTES;
-constexpr int S_OFF_V = S_OFF_K + S_KST * S_HALF;          // 2 stages
-constexpr int S_OFF_C = S_OFF_V + 2 * S_HALF;              // key codes (they travel with K)
+constexpr int S_OFF_V = S_OFF_K + S_KST * S_HALF;
+constexpr int S_OFF_C = S_OFF_V + S_VST * S_HALF;          // key codes (they travel with K)
 constexpr int S_OFF_BAR = S_OFF_C + S_KST * S_CODES;
-constexpr int S_SMEM = S_OFF_BAR + 128 + 1024;
-constexpr int S_THREADS = 160;                             // 4 softmax warps + 1 issuer warp
+constexpr int S_OFF_X = S_OFF_BAR + 128;                   // epilogue exchange of (m, l) between the two halves: 2 KB
+constexpr int S_SMEM = S_OFF_X + 2048 + 1024;
+constexpr int S_THREADS = 288;                             // 8 softmax warps + 1 issuer warp
 
 struct FwdParams {
     int B, L, Lp, n_q, n_kv, P, q_tiles;
@@ -259,6 +301,7 @@ struct FwdParams {
     float* lse;
     uint32_t* keep;   // [B * n_q][q_tiles][Lp / 32][128] keep words (written when dropout is on)
     DropParams drop;  // attention-probability dropout (8-bit threshold); thresh == 0: off
+    Trace tr;
 };
 
 __device__ __forceinline__ int4 lds_int4(uint32_t saddr) {
@@ -298,10 +341,13 @@ __device__ __forceinline__ float mask_max32(uint32_t* s, uint32_t ka, uint32_t k
 // head, query, key) is clear; the row sum l keeps the undropped P (softmax normalisation happens before dropout) and the
 // 1/keep scale is folded into the final O / l.
 //
-// Two CTAs per SM, 256 TMEM columns each: S is double-buffered ([0,64) and [64,128); P, packed bf16 pairs, overwrites the
-// first 32 columns of the buffer its scores came from), O in [128,192).  S(n+2) is issued right behind PV(n) — the tensor
-// pipe runs the MMAs of one thread in order, so the write follows PV(n)'s read of P(n) — which means S(n+1) is already
-// in TMEM when the softmax warps finish tile n: they never wait for the S round trip.
+// Two CTAs per SM, 256 TMEM columns each.  S is double-buffered ([0,64) and [64,128); P, packed bf16 pairs, overwrites
+// columns of the buffer its scores came from): S(n+2) is issued right behind PV(n) — the tensor pipe runs the MMAs
+// of one thread in order, so the write follows PV(n)'s read of P(n) — which means S(n+1) is already in TMEM when the
+// softmax warps finish tile n.  The 64 keys of a tile are split between two softmax warpgroups (8 warps, one query row
+// and 32 keys per thread) that run INDEPENDENT online softmaxes — own running max, own row sum, own accumulator
+// (O_A in [128,192) over the first halves of all tiles, O_B in [192,256) over the second halves) — merged once in the
+// epilogue, so the warpgroups never exchange anything per tile and the SM holds 16 softmax warps.
 template <int KIND, bool DROP>
 __global__ void __launch_bounds__(S_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -310,15 +356,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_OFF_BAR);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;   // [3] K tile + key codes
-    uint64_t* v_full = bars + 4;   // [2]
-    uint64_t* s_full = bars + 6;   // [2] one per S buffer
-    uint64_t* p_full = bars + 8;   // [2] P tile in TMEM (and O rescaled), one per S buffer: the softmax warps can be a
+    uint64_t* k_full = bars + 1;   // [4] K tile + key codes
+    uint64_t* v_full = bars + 5;   // [3]
+    uint64_t* s_full = bars + 8;   // [2] one per S buffer
+    uint64_t* p_full = bars + 10;  // [2] P tile in TMEM (and O rescaled), one per S buffer: the softmax warps can be a
                                    // whole tile ahead of the issuer, and a parity wait must never fall two phases behind
-    uint64_t* pv_done = bars + 10; // PV(n) complete
-    uint64_t* o_full = bars + 11;  // the last PV complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    int* range_slot = reinterpret_cast<int*>(bars + 13);   // [lo, hi) in 64-key tiles
+    uint64_t* pv_done = bars + 12; // PV(n) complete
+    uint64_t* o_full = bars + 13;  // the last PV complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    int* range_slot = reinterpret_cast<int*>(bars + 15);   // [lo, hi) in 64-key tiles
+    float* xch = reinterpret_cast<float*>(smem + S_OFF_X);  // epilogue exchange: [2 halves][m | l][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work item: heaviest query tiles first
@@ -334,10 +381,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         prefetch_tmap(&tmK);
         prefetch_tmap(&tmV);
         prefetch_tmap(&tmO);
-        for (int i = 0; i < 12; ++i) mbar_init(&bars[i], (i == 8 || i == 9) ? 128 : 1);
+        for (int i = 0; i < 14; ++i) mbar_init(&bars[i], (i == 10 || i == 11) ? 256 : 1);
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc<256>(tmem_slot);
         // Key-tile range of this CTA: leading tiles without a valid key (left padding) and trailing tiles that no query of
         // the tile can see are never loaded.  Lane t looks at 64-key tiles t and t + 32.
@@ -387,10 +434,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sq = smem_u32(smem + S_OFF_Q);
     constexpr uint32_t T_O = 128;
 
-    if (warp == 4) {
-        // ===================== issuer: TMA loads + MMAs =====================
-        if (lane == 0) {
-            auto load_k = [&](int n) {  // n-th tile of the range: K and its key codes
+    if (warp == 8) {
+        // ===================== issuer: TMA loads + MMAs (converged warp, elected lane issues) =====================
+        auto load_k = [&](int n) {  // n-th tile of the range: K and its key codes
+            if (elect_one()) {
                 const int st = n % S_KST, j = kt_lo + n;
                 uint8_t* sc = smem + S_OFF_C + st * S_CODES;
                 mbar_expect_tx(&k_full[st], S_HALF + 512 + 32);
@@ -398,60 +445,84 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 bulk_load_1d(sc, p.ka + (long long)b * p.Lp + j * S_KT, 256, &k_full[st]);
                 bulk_load_1d(sc + 256, p.ks + (long long)b * p.Lp + j * S_KT, 256, &k_full[st]);
                 bulk_load_1d(sc + 512, p.blk + ((long long)b * p.Lp >> 5) + 2 * j, 32, &k_full[st]);
-            };
-            auto load_v = [&](int n) {
-                const int st = n & 1;
+            }
+            __syncwarp();
+        };
+        auto load_v = [&](int n) {
+            if (elect_one()) {
+                const int st = n % S_VST;
                 mbar_expect_tx(&v_full[st], S_HALF);
                 tma_load_3d(smem + S_OFF_V + st * S_HALF, &tmV, &v_full[st], g * D, (kt_lo + n) * S_KT, b);
-            };
-            auto issue_s = [&](int n) {  // S(n)[128 x 64] = Q K_n^T into buffer n & 1
-                constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-                const uint32_t sk = smem_u32(smem + S_OFF_K + (n % S_KST) * S_HALF);
-                mbar_wait(&k_full[n % S_KST], (n / S_KST) & 1);
-                tc_fence_after();
+            }
+            __syncwarp();
+        };
+        auto issue_s = [&](int n) {  // S(n)[128 x 64] = Q K_n^T into buffer n & 1
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(&k_full[n % S_KST], (n / S_KST) & 1);
+            tc_fence_after();
+            const uint64_t da = desc_k(sq), db = desc_k(smem_u32(smem + S_OFF_K + (n % S_KST) * S_HALF));
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + (n & 1) * 64, desc_k(sq + k * 32), desc_k(sk + k * 32), idesc, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (n & 1) * 64, da + 2 * k, db + 2 * k, idesc, k != 0);
                 umma_commit(&s_full[n & 1]);
-            };
-            auto issue_pv = [&](int n) {  // O[128 x 64] (+)= P(n)[128 x 64 keys] (TMEM) V_n[64 keys x 64]
-                constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
-                const uint32_t sv = smem_u32(smem + S_OFF_V + (n & 1) * S_HALF);
+            }
+            __syncwarp();
+        };
+        // O_A[128 x 64] (+)= P(n)[:, 0:32] V_n[0:32], O_B (+)= P(n)[:, 32:64] V_n[32:64]; each half's P (16 packed columns)
+        // sits at the start of that half's 32 score columns
+        auto issue_pv = [&](int n, bool last) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+            const uint64_t db = desc_mn(smem_u32(smem + S_OFF_V + (n % S_VST) * S_HALF), S_HALF);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16_ts(tmem_base + T_O, tmem_base + (n & 1) * 64 + k * 8, desc_mn(sv + k * 2048, S_HALF), idesc,
-                                 (n > 0 || k != 0) ? 1u : 0u);
+                    umma_bf16_ts(tmem_base + T_O + (k >> 1) * 64, tmem_base + (n & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                                 db + k * 128, idesc, (n > 0 || (k & 1) != 0) ? 1u : 0u);
                 umma_commit(pv_done);
-            };
-            if (nkt > 0) {
+                if (last) umma_commit(o_full);
+            }
+            __syncwarp();
+        };
+        if (nkt > 0) {
+            if (elect_one()) {
                 mbar_expect_tx(q_full, TILE_BYTES);
                 tma_load_3d(smem + S_OFF_Q, &tmQ, q_full, h * D, qt * BT, b);
-                for (int n = 0; n < S_KST && n < nkt; ++n) load_k(n);
-                load_v(0);
-                if (nkt > 1) load_v(1);
-                mbar_wait(q_full, 0);
-                issue_s(0);
-                if (nkt > 1) issue_s(1);
-                for (int n = 0; n < nkt; ++n) {
-                    mbar_wait(&p_full[n & 1], (n >> 1) & 1);   // S(n) consumed, P(n) in TMEM
-                    if (n + S_KST < nkt) load_k(n + S_KST);         // the K stage of tile n is dead
-                    if (n >= 1 && n + 1 < nkt) {   // V(n+1) goes into the stage PV(n-1) read (issued a whole tile ago)
-                        mbar_wait(pv_done, (n - 1) & 1);
-                        load_v(n + 1);
-                    }
-                    mbar_wait(&v_full[n & 1], (n >> 1) & 1);
-                    tc_fence_after();
-                    issue_pv(n);
-                    if (n + 2 < nkt) issue_s(n + 2);   // into the buffer PV(n) reads P from: ordered behind it
-                    if (n + 1 == nkt) umma_commit(o_full);
+            }
+            __syncwarp();
+            for (int n = 0; n < S_KST && n < nkt; ++n) load_k(n);
+            for (int n = 0; n < S_VST && n < nkt; ++n) load_v(n);
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            if (nkt > 1) issue_s(1);
+            Trace tr = p.tr;
+            if (blockIdx.x != 0 || lane != 0) tr.buf = nullptr;
+            int tn = 0;
+            for (int n = 0; n < nkt; ++n) {
+                trace_pt(tr, 0, tn, 1);
+                mbar_wait(&p_full[n & 1], (n >> 1) & 1);   // S(n) consumed, P(n) in TMEM
+                trace_pt(tr, 0, tn, 2);
+                // loads run two tiles ahead: K(n+4) into the stage of K(n) (S(n) has been consumed), V(n+2) into the stage
+                // PV(n-1) read (issued a whole tile ago)
+                if (n + S_KST < nkt) load_k(n + S_KST);
+                if (n >= 1 && n + S_VST - 1 < nkt) {
+                    mbar_wait(pv_done, (n - 1) & 1);
+                    load_v(n + S_VST - 1);
                 }
+                mbar_wait(&v_full[n % S_VST], (n / S_VST) & 1);
+                tc_fence_after();
+                issue_pv(n, n + 1 == nkt);
+                trace_pt(tr, 0, tn, 3);
+                if (n + 2 < nkt) issue_s(n + 2);   // into the buffer PV(n) reads P from: ordered behind it
+                trace_pt(tr, 0, tn, 4);
             }
         }
     } else {
-        // ===================== softmax: one query row per thread =====================
-        const int row = threadIdx.x;
-        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const uint32_t t_o = t_row + T_O;
+        // ===================== softmax: one query row and one 32-key half of every tile per thread =====================
+        const int hf = warp >> 2;                  // which half of the 64-key tiles (and which accumulator)
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const uint32_t t_o = t_row + T_O + hf * 64;
         const int i = qt * BT + row;
         int act_i = 0, sess_i = 0;
         if (i < p.L) {
@@ -469,134 +540,153 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float m = -INFINITY, l = 0.f;
         int kst = 0;
         uint32_t kph = 0;
+        Trace tr = p.tr;
+        if (blockIdx.x != 0 || threadIdx.x != 0) tr.buf = nullptr;
+        int tn = 0;
+        trace_pt(tr, 1, tn, 19);
         for (int n = 0; n < nkt; ++n) {
-            const int j = kt_lo + n;
+            const int j0 = (kt_lo + n) * S_KT + hf * 32;   // first key of this thread's block
             const uint8_t* sc = smem + S_OFF_C + kst * S_CODES;
             const uint32_t t_s = t_row + (n & 1) * 64;
+            trace_pt(tr, 1, tn, 20);
             mbar_wait(&k_full[kst], kph);   // key codes of this stage
-            int mode[2];
-#pragma unroll
-            for (int bk = 0; bk < 2; ++bk)
-                mode[bk] = classify_block<KIND>(reinterpret_cast<const int4*>(sc + 512)[bk], wr, j * S_KT + bk * 32);
+            trace_pt(tr, 1, tn, 21);
+            const int mode = classify_block<KIND>(reinterpret_cast<const int4*>(sc + 512)[hf], wr, j0);
             mbar_wait(&s_full[n & 1], (n >> 1) & 1);
+            trace_pt(tr, 1, tn, 22);
             tc_fence_after();
-            uint32_t s[64];
-            tmem_ld_32x32(t_s, s);
-            tmem_ld_32x32(t_s + 32, s + 32);
-            tmem_ld_wait();
-            float mx = -INFINITY;
+            uint32_t s[32];
+            bool rescale = false;
+            float m_old = m, m_new = m;
+            if (mode != BLK_SKIP) {   // (a skipped block leaves m, l and the accumulator alone and contributes P = 0)
+                tmem_ld_32x32(t_s + hf * 32, s);
+                tmem_ld_wait();
+                const uint32_t ka = smem_u32(sc) + hf * 128, ks = ka + 256;
+                float mx;
+                if (mode == BLK_FULL) mx = max32(s);
+                else if (mode == BLK_MASK) mx = mask_max32<KIND, false>(s, ka, ks, act_i, sess_i, j0, i, istart);
+                else mx = mask_max32<KIND, true>(s, ka, ks, act_i, sess_i, j0, i, istart);
+                // lazy running max (log2 domain): raise it only from -inf or by more than 2^64
+                const float m_tile = mx * p.scale_log2;
+                if (m == -INFINITY) m_new = m_tile;
+                else if (m_tile > m + 64.f) m_new = m_tile;
+                rescale = (m != -INFINITY) && (m_new != m);
+                if (rescale) l *= ex2_approx(m - m_new);
+                m = m_new;
+                const float neg_m = (m == -INFINITY) ? 0.f : -m;
+                const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_m, neg_m);
+                float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int bk = 0; bk < 2; ++bk) {
-                const uint32_t ka = smem_u32(sc) + bk * 128, ks = ka + 256;
-                const int j0 = j * S_KT + bk * 32;
-                if (mode[bk] == BLK_FULL) mx = fmaxf(mx, max32(s + bk * 32));
-                else if (mode[bk] == BLK_MASK) mx = fmaxf(mx, mask_max32<KIND, false>(s + bk * 32, ka, ks, act_i, sess_i, j0, i, istart));
-                else if (mode[bk] == BLK_MASK_DIAG) mx = fmaxf(mx, mask_max32<KIND, true>(s + bk * 32, ka, ks, act_i, sess_i, j0, i, istart));
-            }
-            // lazy running max (log2 domain): raise it only from -inf or by more than 2^64
-            const float m_tile = mx * p.scale_log2;
-            float m_new = m;
-            if (m == -INFINITY) m_new = m_tile;
-            else if (m_tile > m + 64.f) m_new = m_tile;
-            const bool rescale = (m != -INFINITY) && (m_new != m);
-            if (rescale) l *= ex2_approx(m - m_new);
-            const float m_old = m;
-            m = m_new;
-            const float neg_m = (m == -INFINITY) ? 0.f : -m;
-            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_m, neg_m);
-            float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int bk = 0; bk < 2; ++bk) {
-                uint32_t* pk = s + bk * 16;   // packed pairs of block bk (block 0 packs in place, block 1 into [16, 32))
-                if (mode[bk] == BLK_SKIP) {
-#pragma unroll
-                    for (int w = 0; w < 16; ++w) pk[w] = 0u;
-                } else {
-                    float2 sb = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        const float2 x = __ffma2_rn(u2f2(s[bk * 32 + c], s[bk * 32 + c + 1]), sc2, nm2);
-                        const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-                        sb = __fadd2_rn(sb, e);
-                        pk[c >> 1] = pack_bf16(e.x, e.y);
-                    }
-                    sum = __fadd2_rn(sum, sb);
-                    if constexpr (DROP) {
-                        const uint32_t kw = keep_word(kg, bh, (uint32_t)i, (uint32_t)(2 * j + bk));
-                        keep_row[(size_t)(2 * j + bk) * BT] = kw;
-                        keep_apply_packed(pk, kw);
-                    }
+                for (int c = 0; c < 32; c += 2) {
+                    const float2 x = __ffma2_rn(u2f2(s[c], s[c + 1]), sc2, nm2);
+                    const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    sum = __fadd2_rn(sum, e);
+                    s[c >> 1] = pack_bf16(e.x, e.y);
                 }
+                l += sum.x + sum.y;
+                if constexpr (DROP) {
+                    const uint32_t jw = (uint32_t)(2 * (kt_lo + n) + hf);
+                    const uint32_t kw = keep_word(kg, bh, (uint32_t)i, jw);
+                    keep_row[(size_t)jw * BT] = kw;
+                    keep_apply_packed(s, kw);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) s[w] = 0u;
             }
-            l += sum.x + sum.y;
             if (n > 0 && __any_sync(0xffffffffu, rescale)) {   // cold path: O must be stable, i.e. PV(n-1) complete
                 mbar_wait(pv_done, (n - 1) & 1);
                 tc_fence_after();
                 rescale_o_row64(t_o, rescale ? ex2_approx(m_old - m_new) : 1.f);
             }
-            tmem_st_32x32(t_s, s);
+            trace_pt(tr, 1, tn, 23);
+            tmem_st_32x16(t_s + hf * 32, s);   // over the first 16 of this half's own (already read) score columns
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[n & 1]);
+            trace_pt(tr, 1, tn, 24);
             if (++kst == S_KST) {
                 kst = 0;
                 kph ^= 1;
             }
         }
-        // ---- epilogue: O / l (or the V column mean on uniform rows) -> bf16 -> smem (the dead Q tile) -> TMA store
+        // ---- epilogue: merge the two halves, O / l (or the V column mean on uniform rows) -> bf16 -> smem (the dead Q
+        // tile) -> TMA store.  Thread (row, hf) writes head-dim columns [32 hf, 32 hf + 32).
+        xch[hf * 256 + row] = m;
+        xch[hf * 256 + 128 + row] = l;
         if (nkt > 0) {
             mbar_wait(o_full, 0);
             tc_fence_after();
         }
-        const bool uniform = !(l > 0.f);
-        const float inv = uniform ? 0.f : (DROP ? drop.scale : 1.f) / l;
-        const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
+        named_bar_sync(1, 256);
+        trace_pt(tr, 1, tn, 25);
+        const float m_o = xch[(hf ^ 1) * 256 + row], l_o = xch[(hf ^ 1) * 256 + 128 + row];
+        const float m_all = fmaxf(m, m_o);
+        const float w_me = (m == -INFINITY) ? 0.f : ex2_approx(m - m_all);
+        const float w_ot = (m_o == -INFINITY) ? 0.f : ex2_approx(m_o - m_all);
+        const float l_all = l * w_me + l_o * w_ot;
+        const bool uniform = !(l_all > 0.f);
+        const float inv = uniform ? 0.f : (DROP ? drop.scale : 1.f) / l_all;
+        const float wa = (hf == 0 ? w_me : w_ot) * inv, wb = (hf == 0 ? w_ot : w_me) * inv;   // weights of O_A, O_B
+        const float* vm = p.vmean + ((long long)b * p.n_kv + g) * D + hf * 32;
+        {
+            uint32_t oa[32], ob[32];
             if (nkt > 0) {
-                tmem_ld_32x32(t_o + hh * 32, o);
+                tmem_ld_32x32(t_row + T_O + hf * 32, oa);
+                tmem_ld_32x32(t_row + T_O + 64 + hf * 32, ob);
                 tmem_ld_wait();
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = uniform ? vm[hh * 32 + 8 * q + e] : __uint_as_float(o[8 * q + e]) * inv;
-                const int ch = hh * 4 + q;
+                for (int e = 0; e < 8; ++e) {
+                    // an accumulator no PV ever wrote (its half was skipped in every tile) holds garbage: weight exactly 0
+                    const float a = (wa != 0.f) ? __uint_as_float(oa[8 * q + e]) * wa : 0.f;
+                    const float c = (wb != 0.f) ? __uint_as_float(ob[8 * q + e]) * wb : 0.f;
+                    v[e] = uniform ? vm[8 * q + e] : a + c;
+                }
+                const int ch = hf * 4 + q;
                 const bf16x8 ov = float_to_bf16x8(v);
                 sts128(sq + row * 128 + ((ch ^ (row & 7)) << 4), ov.u[0], ov.u[1], ov.u[2], ov.u[3]);
             }
         }
-        if (i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m + log2f(l));
+        if (hf == 0 && i < p.L) p.lse[((long long)b * p.n_q + h) * p.L + i] = uniform ? INFINITY : (m_all + log2f(l_all));
         tc_fence_before();
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (threadIdx.x == 0) {
             tma_store_3d(&tmO, smem + S_OFF_Q, h * D, qt * BT, b);
             bulk_commit();
             bulk_wait0();
+            trace_pt(tr, 1, tn, 26);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<256>(tmem_base);
+    if (warp == 8) tmem_dealloc<256>(tmem_base);
 }
 
 // =================================================================================================================
 // backward
 // =================================================================================================================
-constexpr int B_KV_STAGE = 2 * TILE_BYTES;                 // K | V
+constexpr int B_KV_META = 2048;                            // ka[128] | ks[128] | blk[4] int4 (+ pad: stages stay 1 KB aligned)
+constexpr int B_KV_STAGE = 2 * TILE_BYTES + B_KV_META;     // K | V | codes
 constexpr int B_OFF_KV = 0;                                // 2 stages (items)
-constexpr int B_QST = 3;                                   // Q | dO stages (steps)
-constexpr int B_QDO_STAGE = 2 * TILE_BYTES;
-constexpr int B_OFF_QDO = 2 * B_KV_STAGE;
-constexpr int B_OFF_P = B_OFF_QDO + B_QST * B_QDO_STAGE;   // [128 q x 128 k] bf16 in two 64-key halves
+constexpr int B_QDO_ROWS = 2048;                           // lse'[128] | dsum'[128] | level[128] | session[128]
+constexpr int B_QDO_KEEP = 2048;                           // keep words [4 blocks][128 rows]
+constexpr int B_QDO_STAGE = 2 * TILE_BYTES + B_QDO_ROWS + B_QDO_KEEP;   // Q | dO | row scalars | keep words
+constexpr int B_OFF_QDO = 2 * B_KV_STAGE;                  // 2 stages
+constexpr int B_OFF_P = B_OFF_QDO + 2 * B_QDO_STAGE;       // [128 q x 128 k] bf16 in two 64-key halves
 constexpr int B_OFF_DS = B_OFF_P + 2 * TILE_BYTES;
-constexpr int B_OFF_BAR = B_OFF_DS + 2 * TILE_BYTES;
+constexpr int B_OFF_STG = B_OFF_DS + 2 * TILE_BYTES;       // 16 KB staging: dQ half tiles (fp32), dK / dV tiles (bf16)
+constexpr int B_OFF_BAR = B_OFF_STG + TILE_BYTES;
 constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
 constexpr int B_THREADS = 512;                             // producer, issuer, 2 spare | 8 softmax / dS warps | 4 drain warps
+constexpr int DQ_TILE_FLOATS = BT * D;
 static_assert(B_SMEM <= 227 * 1024, "backward shared memory");
+static_assert(B_KV_STAGE % 1024 == 0 && B_QDO_STAGE % 1024 == 0 && B_OFF_P % 1024 == 0 && B_OFF_STG % 1024 == 0,
+              "SWIZZLE_128B tiles need 1024-byte aligned bases");
 
 struct BwdParams {
     int B, L, Lp, n_q, n_kv, P, q_tiles, k_tiles, total;
@@ -605,95 +695,52 @@ struct BwdParams {
     const int4* blk;
     const int* qa;
     const int* qs;       // [B, Lp] query-side behaviour level / session (zero past L)
-    const float* lse_p;  // [B, n_q, Lp] log2 domain plus log2(keep_prob); +inf = uniform row or i >= L
-    const float* dsum_p; // [B, n_q, Lp] rowsum(dO o O) * keep_prob (uniform rows: unscaled)
+    const float* lse_p;  // [B, n_q, Lp] log2 domain minus log2(1/keep); +inf = uniform row or i >= L
+    const float* dsum_p; // [B, n_q, Lp] rowsum(dO o O) * keep (uniform rows: unscaled)
     const unsigned* uni_bits;  // [B]: bit qt = query tile qt holds a uniform row
     const uint32_t* keep;      // the forward's keep words
     float scale, scale_log2, inv_L;
-    float* dq_acc;       // [B * n_q][Lp][64] fp32 partial sums of dQ
-    bf16* dq;            // [B * L, ld_d]: written in-kernel for the groups a CTA owns
-    long long ld_d;
-    bf16* dk;
-    bf16* dv;
+    float* dq_acc;       // [B, n_q, q_tiles][2 halves][128 rows][32 floats], 16-byte chunks XOR-swizzled by (row & 7)
     int drop_on;
+    Trace tr;
 };
 
-// Work order.  A "group" = (sequence, kv head); its k_tiles items share Q / dO tiles and dQ tiles.
-//  * owned groups (full rounds): groups are dealt one per CTA and a CTA walks ITS group's key tiles 0..k_tiles-1 back to
-//    back (w advances by gridDim.x between its items): every CTA carries the same load, the group's tiles stay in L2, and —
-//    since every contribution to a dQ tile of the group comes from this CTA, from the same thread per row — dQ needs no
-//    atomics: the first key tile stores the partial sum, later ones add to it, the last one adds, converts and writes bf16;
-//  * the last (n_groups mod gridDim.x) groups are dealt key-tile-major over all CTAs, heaviest key tile first (tile 0
-//    meets the most query tiles), so the tail of the launch is made of the light items; their dQ goes through fp32 RED
-//    into a zeroed accumulator and a small convert kernel.
 template <int KIND>
-struct Cursor {
-    int w, b, g, kt, hh;
-    unsigned qmask, qm, uni;
-    bool valid, owned;
-    __device__ __forceinline__ void load_item(const BwdParams& p) {
-        valid = w < p.total;
-        if (!valid) return;
-        const int grid = (int)gridDim.x;
-        const int n_groups = p.B * p.n_kv;
-        const int full = (n_groups / grid) * grid;
-        int grp;
-        owned = w < full * p.k_tiles;
-        if (owned) {
-            const int r = w % (grid * p.k_tiles);
-            kt = r / grid;
-            grp = (w / (grid * p.k_tiles)) * grid + r % grid;
-        } else {
-            const int wr = w - full * p.k_tiles, rem = n_groups - full;
-            kt = wr / rem;
-            grp = full + wr % rem;
-        }
-        b = grp / p.n_kv;
-        g = grp % p.n_kv;
-        const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
-        uni = p.uni_bits[b] & all;
-        if (kind_causal<KIND>()) qmask = ((all >> kt) << kt) | uni;
-        else qmask = all;
-        qm = qmask;
-        hh = 0;
+__device__ __forceinline__ void bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask) {
+    // Work order.  A "group" = (sequence, kv head); its k_tiles items share Q / dO tiles and dQ accumulator tiles.
+    //  * full rounds: groups are dealt one per CTA and a CTA walks ITS group's key tiles 0..k_tiles-1 back to back (w
+    //    advances by gridDim.x between its items): every CTA carries the same load, and the group's tiles stay in L2;
+    //  * the last (n_groups mod gridDim.x) groups are dealt key-tile-major over all CTAs, heaviest key tile first (tile 0
+    //    meets the most query tiles), so the tail of the launch is made of the light items.
+    const int grid = (int)gridDim.x;
+    const int n_groups = p.B * p.n_kv;
+    const int full = (n_groups / grid) * grid;
+    int grp;
+    if (w < full * p.k_tiles) {
+        const int r = w % (grid * p.k_tiles);
+        kt = r / grid;
+        grp = (w / (grid * p.k_tiles)) * grid + r % grid;
+    } else {
+        const int wr = w - full * p.k_tiles, rem = n_groups - full;
+        kt = wr / rem;
+        grp = full + wr % rem;
     }
-    __device__ __forceinline__ void init(const BwdParams& p) {
-        w = blockIdx.x;
-        load_item(p);
-    }
-    __device__ __forceinline__ int qt() const { return __ffs(qm) - 1; }
-    __device__ __forceinline__ int n_steps() const { return 2 * __popc(qmask); }
-    // -> true when the cursor moved to a new item (or past the end)
-    __device__ __forceinline__ bool advance(const BwdParams& p) {
-        qm &= qm - 1;
-        if (qm) return false;
-        if (hh == 0) {
-            hh = 1;
-            qm = qmask;
-            return false;
-        }
-        w += gridDim.x;
-        load_item(p);
-        return true;
-    }
-    // last key tile that contributes to query tile q of this group
-    __device__ __forceinline__ int last_kt(const BwdParams& p, int q) const {
-        if (kind_causal<KIND>() && !((uni >> q) & 1u)) return q;
-        return p.k_tiles - 1;
-    }
-};
-
-__device__ __forceinline__ int4 ldg_int4(const int* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+    b = grp / p.n_kv;
+    g = grp % p.n_kv;
+    const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
+    if (kind_causal<KIND>()) qmask = ((all >> kt) << kt) | (p.uni_bits[b] & all);
+    else qmask = all;
+}
 
 // One 32-key block of a backward step, for one query row.  In: s = scores (raw words), dp = dO V^T.  Out: pk = the dV
 // operand (P with dropout and 1/keep applied) and ds = the dK / dQ operand, both as 16 packed bf16 pairs.
 //   Pz = exp2(s * scale_log2 - lse') = P / keep_prob (uniform rows: 1/L on every key j < L, no dropout)
 //   dS = (Pz o keep) o dP - Pz * dsum'   with dsum' = rowsum(dO o O) * keep_prob (uniform rows: unscaled)
 // MODE: BLK_FULL (no predicate, no uniform row in the warp), BLK_MASK / BLK_MASK_DIAG (predicate per element, uniform rows
-// handled; ka / ks = the block's key codes in global memory), BLK_SKIP is handled by the caller.
+// handled), BLK_SKIP is handled by the caller.
 template <int KIND, bool DROP, int MODE>
-__device__ __forceinline__ void bwd_block(const uint32_t* s, const uint32_t* dp, uint32_t* pk, uint32_t* ds, const int* ka,
-                                          const int* ks, int act_i, int sess_i, int j0, int i, int istart, float scale_log2,
+__device__ __forceinline__ void bwd_block(const uint32_t* s, const uint32_t* dp, uint32_t* pk, uint32_t* ds, uint32_t ka,
+                                          uint32_t ks, int act_i, int sess_i, int j0, int i, int istart, float scale_log2,
                                           float neg_lse, float neg_dsum, float pu, int lim_u, uint32_t kw) {
     const float2 sc2 = make_float2(scale_log2, scale_log2), nl2 = make_float2(neg_lse, neg_lse);
     const float2 nd2 = make_float2(neg_dsum, neg_dsum);
@@ -708,8 +755,8 @@ __device__ __forceinline__ void bwd_block(const uint32_t* s, const uint32_t* dp,
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
             int4 a4 = make_int4(0, 0, 0, 0), s4 = make_int4(0, 0, 0, 0);
-            if (KIND != MASK_SESSION) a4 = ldg_int4(ka + c4 * 4);
-            if (kind_uses_sess<KIND>()) s4 = ldg_int4(ks + c4 * 4);
+            if (KIND != MASK_SESSION) a4 = lds_int4(ka + c4 * 16);
+            if (kind_uses_sess<KIND>()) s4 = lds_int4(ks + c4 * 16);
             const int av[4] = {a4.x, a4.y, a4.z, a4.w};
             const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
             float v[4];
@@ -746,58 +793,30 @@ __device__ __forceinline__ void bwd_block(const uint32_t* s, const uint32_t* dp,
     }
 }
 
-// per-row inputs of a step, fetched one step ahead (coalesced: consecutive rows = consecutive lanes)
-struct RowData {
-    float lse, dsum;
-    int act, sess;
-    uint32_t kw0, kw1;
-};
-template <int KIND, bool DROP>
-__device__ __forceinline__ RowData load_row(const BwdParams& p, const Cursor<KIND>& c, int row, int wgi) {
-    RowData r;
-    const int qt = c.qt();
-    const long long bh = (long long)c.b * p.n_q + 2 * c.g + c.hh;
-    const long long ro = bh * p.Lp + qt * BT + row;
-    r.lse = __ldg(p.lse_p + ro);
-    r.dsum = __ldg(p.dsum_p + ro);
-    r.act = kind_uses_act<KIND>() ? __ldg(p.qa + (long long)c.b * p.Lp + qt * BT + row) : 0;
-    r.sess = kind_uses_sess<KIND>() ? __ldg(p.qs + (long long)c.b * p.Lp + qt * BT + row) : 0;
-    r.kw0 = r.kw1 = 0xffffffffu;
-    if constexpr (DROP) {
-        const uint32_t* kp = p.keep + ((size_t)(bh * p.q_tiles + qt) * (size_t)(p.Lp >> 5) + 4 * c.kt + 2 * wgi) * BT + row;
-        r.kw0 = __ldg(kp);
-        r.kw1 = __ldg(kp + BT);
-    }
-    return r;
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int KIND, bool DROP>
 __global__ void __launch_bounds__(B_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, BwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV, BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
     uint64_t* kv_full = bars + 0;    // [2]
     uint64_t* kv_free = bars + 2;    // [2]
-    uint64_t* qdo_full = bars + 4;   // [3]
-    uint64_t* qdo_free = bars + 7;   // [3]
-    uint64_t* s_full = bars + 10;
-    uint64_t* s_free = bars + 11;    // all softmax threads have read S
-    uint64_t* dp_full = bars + 12;
-    uint64_t* dp_free = bars + 13;   // all softmax threads have read dP
-    uint64_t* pds_full = bars + 14;  // P and dS tiles written
-    uint64_t* p_free = bars + 15;
-    uint64_t* ds_free = bars + 16;
-    uint64_t* dq_full = bars + 17;   // [2]: dQ lives in two TMEM buffers, so dQ(n) does not wait for the drain of dQ(n-1)
-    uint64_t* dq_free = bars + 19;   // [2]
-    uint64_t* dkv_full = bars + 21;
-    uint64_t* dkv_free = bars + 22;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+    uint64_t* qdo_full = bars + 4;   // [2]
+    uint64_t* qdo_free = bars + 6;   // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_free = bars + 9;     // all softmax threads have read S
+    uint64_t* dp_full = bars + 10;
+    uint64_t* dp_free = bars + 11;   // all softmax threads have read dP
+    uint64_t* pds_full = bars + 12;  // P and dS tiles written
+    uint64_t* p_free = bars + 13;
+    uint64_t* ds_free = bars + 14;
+    uint64_t* dq_full = bars + 15;   // [2]: dQ lives in two TMEM buffers, so dQ(n) does not wait for the drain of dQ(n-1)
+    uint64_t* dq_free = bars + 17;   // [2]
+    uint64_t* dkv_full = bars + 19;
+    uint64_t* dkv_free = bars + 20;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -805,15 +824,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         prefetch_tmap(&tmK);
         prefetch_tmap(&tmV);
         prefetch_tmap(&tmdO);
+        prefetch_tmap(&tmdK);
+        prefetch_tmap(&tmdV);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_free[s], 1);
-            mbar_init(&dq_full[s], 1);
-            mbar_init(&dq_free[s], 128);
-        }
-        for (int s = 0; s < B_QST; ++s) {
             mbar_init(&qdo_full[s], 1);
             mbar_init(&qdo_free[s], 1);
+            mbar_init(&dq_full[s], 1);
+            mbar_init(&dq_free[s], 128);
         }
         mbar_init(s_full, 1);
         mbar_init(s_free, 256);
@@ -833,117 +852,105 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448) and [448,512)
     constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+    constexpr uint32_t QDO_TX = 2 * TILE_BYTES + B_QDO_ROWS + (DROP ? B_QDO_KEEP : 0);
 
-    if (warp < 4) {
-        reg_dealloc<64>();
-        if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
-            uint32_t item_n = 0;
-            int st = 0;
-            uint32_t ph = 0;
-            Cursor<KIND> c;
-            c.init(p);
-            while (c.valid) {
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t item_n = 0, step_n = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+                int b, g, kt;
+                unsigned qmask;
+                bwd_decode<KIND>(w, p, b, g, kt, qmask);
                 const int ks = item_n & 1;
                 uint8_t* skv = smem + B_OFF_KV + ks * B_KV_STAGE;
                 mbar_wait(&kv_free[ks], ((item_n >> 1) & 1) ^ 1);
-                mbar_expect_tx(&kv_full[ks], 2 * TILE_BYTES);
-                tma_load_3d(skv, &tmK, &kv_full[ks], c.g * D, c.kt * BT, c.b);
-                tma_load_3d(skv + TILE_BYTES, &tmV, &kv_full[ks], c.g * D, c.kt * BT, c.b);
-                bool moved = false;
-                while (!moved) {
-                    mbar_wait(&qdo_free[st], ph ^ 1);
-                    uint8_t* sq = smem + B_OFF_QDO + st * B_QDO_STAGE;
-                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
-                    tma_load_3d(sq, &tmQ, &qdo_full[st], (2 * c.g + c.hh) * D, c.qt() * BT, c.b);
-                    tma_load_3d(sq + TILE_BYTES, &tmdO, &qdo_full[st], (2 * c.g + c.hh) * D, c.qt() * BT, c.b);
-                    if (++st == B_QST) {
-                        st = 0;
-                        ph ^= 1;
+                mbar_expect_tx(&kv_full[ks], 2 * TILE_BYTES + 1024 + 64);
+                tma_load_3d(skv, &tmK, &kv_full[ks], g * D, kt * BT, b);
+                tma_load_3d(skv + TILE_BYTES, &tmV, &kv_full[ks], g * D, kt * BT, b);
+                bulk_load_1d(skv + 2 * TILE_BYTES, p.ka + (long long)b * p.Lp + kt * BT, 512, &kv_full[ks]);
+                bulk_load_1d(skv + 2 * TILE_BYTES + 512, p.ks + (long long)b * p.Lp + kt * BT, 512, &kv_full[ks]);
+                bulk_load_1d(skv + 2 * TILE_BYTES + 1024, p.blk + ((long long)b * p.Lp >> 5) + 4 * kt, 64, &kv_full[ks]);
+                for (int hh = 0; hh < 2; ++hh) {
+                    for (unsigned qm = qmask; qm; qm &= qm - 1, ++step_n) {
+                        const int qt = __ffs(qm) - 1;
+                        const int st = step_n & 1;
+                        mbar_wait(&qdo_free[st], ((step_n >> 1) & 1) ^ 1);
+                        uint8_t* sq = smem + B_OFF_QDO + st * B_QDO_STAGE;
+                        mbar_expect_tx(&qdo_full[st], QDO_TX);
+                        tma_load_3d(sq, &tmQ, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
+                        tma_load_3d(sq + TILE_BYTES, &tmdO, &qdo_full[st], (2 * g + hh) * D, qt * BT, b);
+                        const long long bh = (long long)b * p.n_q + 2 * g + hh;
+                        const long long ro = bh * p.Lp + qt * BT;
+                        uint8_t* sr = sq + 2 * TILE_BYTES;
+                        bulk_load_1d(sr, p.lse_p + ro, 512, &qdo_full[st]);
+                        bulk_load_1d(sr + 512, p.dsum_p + ro, 512, &qdo_full[st]);
+                        bulk_load_1d(sr + 1024, p.qa + (long long)b * p.Lp + qt * BT, 512, &qdo_full[st]);
+                        bulk_load_1d(sr + 1536, p.qs + (long long)b * p.Lp + qt * BT, 512, &qdo_full[st]);
+                        if constexpr (DROP)
+                            bulk_load_1d(sr + B_QDO_ROWS,
+                                         p.keep + ((size_t)(bh * p.q_tiles + qt) * (size_t)(p.Lp >> 5) + 4 * kt) * BT,
+                                         B_QDO_KEEP, &qdo_full[st]);
                     }
-                    moved = c.advance(p);
                 }
-                ++item_n;
-            }
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer =====================
-            uint32_t item_n = 0, step_n = 0;
-            int st = 0;           // Q / dO stage of the current step
-            uint32_t ph = 0;
-            const uint32_t sp = smem_u32(smem + B_OFF_P), sds = smem_u32(smem + B_OFF_DS);
-            Cursor<KIND> c;
-            c.init(p);
-            while (c.valid) {
-                const int N = c.n_steps();
-                const int ks = item_n & 1;
-                const uint32_t sk = smem_u32(smem + B_OFF_KV + ks * B_KV_STAGE), sv = sk + TILE_BYTES;
-                mbar_wait(&kv_full[ks], (item_n >> 1) & 1);
-                {   // first step of the item: S and dP (the previous item's last step has released both buffers)
-                    mbar_wait(&qdo_full[st], ph);
-                    if (step_n > 0) {
-                        mbar_wait(s_free, (step_n - 1) & 1);
-                        mbar_wait(dp_free, (step_n - 1) & 1);
-                    }
-                    tc_fence_after();
-                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
-                    issue_nt_128x128x64(tmem_base + T_S, sq, sk);
-                    umma_commit(s_full);
-                    issue_nt_128x128x64(tmem_base + T_DP, sq + TILE_BYTES, sv);
-                    umma_commit(dp_full);
-                }
-                for (int n = 0; n < N; ++n, ++step_n) {
-                    int stn = st + 1;
-                    uint32_t phn = ph;
-                    if (stn == B_QST) {
-                        stn = 0;
-                        phn ^= 1;
-                    }
-                    const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
-                    const uint32_t sqn = smem_u32(smem + B_OFF_QDO + stn * B_QDO_STAGE);
-                    if (n + 1 < N) {
-                        mbar_wait(&qdo_full[stn], phn);
-                        mbar_wait(s_free, step_n & 1);
-                        tc_fence_after();
-                        issue_nt_128x128x64(tmem_base + T_S, sqn, sk);                  // S(n+1) = Q K^T
-                        umma_commit(s_full);
-                        mbar_wait(dp_free, step_n & 1);
-                        tc_fence_after();
-                        issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv);    // dP(n+1) = dO V^T
-                        umma_commit(dp_full);
-                    }
-                    mbar_wait(pds_full, step_n & 1);
-                    if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
-                    tc_fence_after();
-                    issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0);   // dV += P^T dO
-                    umma_commit(p_free);
-                    issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0);               // dK += dS^T Q
-                    const uint32_t db = step_n & 1, du = step_n >> 1;
-                    if (du > 0) {
-                        mbar_wait(&dq_free[db], (du - 1) & 1);
-                        tc_fence_after();
-                    }
-                    umma_commit(&qdo_free[st]);   // Q / dO of this step are dead once dK is done: dQ reads dS and K only
-                    issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false);     // dQ = dS K
-                    umma_commit(&dq_full[db]);
-                    umma_commit(ds_free);
-                    if (n + 1 == N) {
-                        umma_commit(dkv_full);
-                        umma_commit(&kv_free[ks]);
-                    }
-                    st = stn;
-                    ph = phn;
-                }
-                c.w += gridDim.x;
-                c.load_item(p);
-                ++item_n;
             }
         }
-    } else if (warp < 12) {
+    } else if (warp == 1) {
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        uint32_t item_n = 0, step_n = 0;
+        const uint32_t sp = smem_u32(smem + B_OFF_P), sds = smem_u32(smem + B_OFF_DS);
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask;
+            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            const int N = 2 * __popc(qmask);
+            const int ks = item_n & 1;
+            const uint32_t sk = smem_u32(smem + B_OFF_KV + ks * B_KV_STAGE), sv = sk + TILE_BYTES;
+            mbar_wait(&kv_full[ks], (item_n >> 1) & 1);
+            {   // first step of the item: S and dP (the previous item's last step has released both buffers)
+                const int st = step_n & 1;
+                mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                if (step_n > 0) {
+                    mbar_wait(s_free, (step_n - 1) & 1);
+                    mbar_wait(dp_free, (step_n - 1) & 1);
+                }
+                tc_fence_after();
+                const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
+                issue_nt_128x128x64(tmem_base + T_S, sq, sk, s_full);
+                issue_nt_128x128x64(tmem_base + T_DP, sq + TILE_BYTES, sv, dp_full);
+            }
+            for (int n = 0; n < N; ++n, ++step_n) {
+                const int st = step_n & 1;
+                const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
+                const uint32_t sqn = smem_u32(smem + B_OFF_QDO + (st ^ 1) * B_QDO_STAGE);
+                if (n + 1 < N) {
+                    mbar_wait(&qdo_full[st ^ 1], ((step_n + 1) >> 1) & 1);
+                    mbar_wait(s_free, step_n & 1);
+                    tc_fence_after();
+                    issue_nt_128x128x64(tmem_base + T_S, sqn, sk, s_full);                   // S(n+1) = Q K^T
+                    mbar_wait(dp_free, step_n & 1);
+                    tc_fence_after();
+                    issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv, dp_full);    // dP(n+1) = dO V^T
+                }
+                mbar_wait(pds_full, step_n & 1);
+                if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
+                tc_fence_after();
+                issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0, p_free);   // dV += P^T dO
+                // Q / dO of this step are dead once dK is done: dQ reads dS and K only
+                issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0, &qdo_free[st]);        // dK += dS^T Q
+                const uint32_t db = step_n & 1, du = step_n >> 1;
+                if (du > 0) {
+                    mbar_wait(&dq_free[db], (du - 1) & 1);
+                    tc_fence_after();
+                }
+                const bool last = n + 1 == N;
+                issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false, &dq_full[db], ds_free,   // dQ = dS K
+                                    last ? dkv_full : nullptr, last ? &kv_free[ks] : nullptr);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
         // ===================== softmax / dS warps: warpgroup k (warps 4+4k..7+4k) owns key columns [64k, 64k+64) of the
-        // tile, processed as two 32-key blocks; one query row per thread.  Both blocks are computed into registers first;
-        // the P / dS tiles are written at the end of the step, a whole step after the MMAs that read the previous ones
-        // were issued. =====================
-        reg_alloc<168>();
+        // tile, processed as two 32-key blocks; one query row per thread =====================
         const int wgi = (warp - 4) >> 2;
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
@@ -953,195 +960,175 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // P / dS live as two 64-key halves; a 32-key block is four 16-byte chunks of this thread's 128-byte row
         const uint32_t sP = smem_u32(smem + B_OFF_P + wgi * TILE_BYTES) + row * 128;
         const uint32_t sDS = smem_u32(smem + B_OFF_DS + wgi * TILE_BYTES) + row * 128;
-        uint32_t step_n = 0;
-        Cursor<KIND> c;
-        c.init(p);
-        RowData rd;
-        if (c.valid) rd = load_row<KIND, DROP>(p, c, row, wgi);
-        int4 bsum0 = make_int4(0, 0, 0, 0), bsum1 = bsum0;
-        bool new_item = true;
-        while (c.valid) {
-            if (new_item) {
-                const int4* bp = p.blk + (((long long)c.b * p.Lp + c.kt * BT) >> 5) + wgi * 2;
-                bsum0 = __ldg(bp);
-                bsum1 = __ldg(bp + 1);
-            }
-            Cursor<KIND> nx = c;
-            new_item = nx.advance(p);
-            RowData rd_next = rd;
-            if (nx.valid) rd_next = load_row<KIND, DROP>(p, nx, row, wgi);
-            const int qt = c.qt();
-            const int i = qt * BT + row;
-            const int jbase = c.kt * BT + wgi * 64;
-            const int* ka = p.ka + (long long)c.b * p.Lp + jbase;
-            const int* kss = p.ks + (long long)c.b * p.Lp + jbase;
-            const float lse_i = rd.lse;
-            const int act_i = rd.act, sess_i = rd.sess;
-            const bool uni = (i < p.L) && (lse_i == INFINITY);
-            const bool wuni = __any_sync(0xffffffffu, uni);
-            const int istart = (i / p.P) * p.P;
-            const WarpRange wr = warp_range<KIND>(i, p.L, p.P, act_i, sess_i);
-            const float pu = uni ? p.inv_L : 0.f;
-            const float neg_lse = -lse_i;       // -inf on uniform / padding rows: exp2 -> 0
-            const float neg_dsum = -rd.dsum;
-            mbar_wait(s_full, step_n & 1);
-            mbar_wait(dp_full, step_n & 1);
-            tc_fence_after();
-            uint32_t pk[32], ds[32];
+        uint32_t item_n = 0, step_n = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask;
+            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            const int ks = item_n & 1;
+            mbar_wait(&kv_full[ks], (item_n >> 1) & 1);  // key codes
+            const uint8_t* meta = smem + B_OFF_KV + ks * B_KV_STAGE + 2 * TILE_BYTES;
+            const uint32_t ka = smem_u32(meta) + wgi * 256, kss = ka + 512;
+            const int4 bsum0 = reinterpret_cast<const int4*>(meta + 1024)[wgi * 2];
+            const int4 bsum1 = reinterpret_cast<const int4*>(meta + 1024)[wgi * 2 + 1];
+            const int jbase = kt * BT + wgi * 64;
+            for (int hh = 0; hh < 2; ++hh) {
+                for (unsigned qm = qmask; qm; qm &= qm - 1, ++step_n) {
+                    const int qt = __ffs(qm) - 1;
+                    const int i = qt * BT + row;
+                    // per-row scalars travel with the Q / dO stage (padded copies: lse' = +inf, dsum' = 0 past L)
+                    const int st = step_n & 1;
+                    mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                    const float* rowf = reinterpret_cast<const float*>(smem + B_OFF_QDO + st * B_QDO_STAGE + 2 * TILE_BYTES);
+                    const float lse_i = rowf[row], dsum_i = rowf[128 + row];
+                    const int act_i = reinterpret_cast<const int*>(rowf)[256 + row];
+                    const int sess_i = reinterpret_cast<const int*>(rowf)[384 + row];
+                    const uint32_t* keep_s = reinterpret_cast<const uint32_t*>(rowf) + 512 + wgi * 2 * BT + row;
+                    const bool uni = (i < p.L) && (lse_i == INFINITY);
+                    const bool wuni = __any_sync(0xffffffffu, uni);
+                    const int istart = (i / p.P) * p.P;
+                    const WarpRange wr = warp_range<KIND>(i, p.L, p.P, act_i, sess_i);
+                    const float pu = uni ? p.inv_L : 0.f;
+                    const float neg_lse = -lse_i;       // -inf on uniform / padding rows: exp2 -> 0
+                    const float neg_dsum = -dsum_i;
+                    mbar_wait(s_full, step_n & 1);
+                    mbar_wait(dp_full, step_n & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int bk = 0; bk < 2; ++bk) {
+                        const int j0 = jbase + bk * 32;
+                        int mode = classify_block<KIND>(bk == 0 ? bsum0 : bsum1, wr, j0);
+                        // uniform rows put 1/L on every key below L, whatever the predicate says
+                        if (wuni && j0 < p.L && (mode == BLK_SKIP || mode == BLK_FULL)) mode = BLK_MASK_DIAG;
+                        uint32_t pk[16], ds[16];
+                        if (mode == BLK_SKIP) {
 #pragma unroll
-            for (int bk = 0; bk < 2; ++bk) {
-                const int j0 = jbase + bk * 32;
-                int mode = classify_block<KIND>(bk == 0 ? bsum0 : bsum1, wr, j0);
-                // uniform rows put 1/L on every key below L, whatever the predicate says
-                if (wuni && j0 < p.L && (mode == BLK_SKIP || mode == BLK_FULL)) mode = BLK_MASK_DIAG;
-                if (mode == BLK_SKIP) {
+                            for (int x = 0; x < 16; ++x) pk[x] = ds[x] = 0u;
+                            if (bk == 1) {   // nothing to read from TMEM: release S and dP
+                                tc_fence_before();
+                                mbar_arrive(s_free);
+                                mbar_arrive(dp_free);
+                            }
+                        } else {
+                            uint32_t s[32], dp[32];
+                            tmem_ld_32x32(t_s + bk * 32, s);
+                            tmem_ld_32x32(t_dp + bk * 32, dp);
+                            tmem_ld_wait();
+                            if (bk == 1) {
+                                tc_fence_before();
+                                mbar_arrive(s_free);
+                                mbar_arrive(dp_free);
+                            }
+                            uint32_t kw = 0xffffffffu;
+                            if constexpr (DROP) kw = uni ? 0xffffffffu : keep_s[bk * BT];
+                            const int lim_u = uni ? (p.L - j0) : 0;
+                            if (mode == BLK_FULL)
+                                bwd_block<KIND, DROP, BLK_FULL>(s, dp, pk, ds, ka + bk * 128, kss + bk * 128, act_i, sess_i, j0, i,
+                                                                istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
+                            else if (mode == BLK_MASK)
+                                bwd_block<KIND, DROP, BLK_MASK>(s, dp, pk, ds, ka + bk * 128, kss + bk * 128, act_i, sess_i, j0, i,
+                                                                istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
+                            else
+                                bwd_block<KIND, DROP, BLK_MASK_DIAG>(s, dp, pk, ds, ka + bk * 128, kss + bk * 128, act_i, sess_i, j0,
+                                                                     i, istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
+                        }
+                        if (bk == 0 && step_n > 0) {
+                            mbar_wait(p_free, (step_n - 1) & 1);
+                            mbar_wait(ds_free, (step_n - 1) & 1);
+                        }
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) pk[bk * 16 + x] = ds[bk * 16 + x] = 0u;
-                    if (bk == 1) {   // nothing to read from TMEM: release S and dP
-                        tc_fence_before();
-                        mbar_arrive(s_free);
-                        mbar_arrive(dp_free);
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t off = (uint32_t)(((bk * 4 + q) ^ (row & 7)) << 4);
+                            sts128(sP + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            sts128(sDS + off, ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+                        }
                     }
-                } else {
-                    uint32_t s[32], dp[32];
-                    tmem_ld_32x32(t_s + bk * 32, s);
-                    tmem_ld_32x32(t_dp + bk * 32, dp);
-                    tmem_ld_wait();
-                    if (bk == 1) {
-                        tc_fence_before();
-                        mbar_arrive(s_free);
-                        mbar_arrive(dp_free);
-                    }
-                    uint32_t kw = 0xffffffffu;
-                    if constexpr (DROP) kw = uni ? 0xffffffffu : (bk == 0 ? rd.kw0 : rd.kw1);
-                    const int lim_u = uni ? (p.L - j0) : 0;
-                    if (mode == BLK_FULL)
-                        bwd_block<KIND, DROP, BLK_FULL>(s, dp, pk + bk * 16, ds + bk * 16, ka + bk * 32, kss + bk * 32, act_i,
-                                                        sess_i, j0, i, istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
-                    else if (mode == BLK_MASK)
-                        bwd_block<KIND, DROP, BLK_MASK>(s, dp, pk + bk * 16, ds + bk * 16, ka + bk * 32, kss + bk * 32, act_i,
-                                                        sess_i, j0, i, istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
-                    else
-                        bwd_block<KIND, DROP, BLK_MASK_DIAG>(s, dp, pk + bk * 16, ds + bk * 16, ka + bk * 32, kss + bk * 32,
-                                                             act_i, sess_i, j0, i, istart, p.scale_log2, neg_lse, neg_dsum, pu,
-                                                             lim_u, kw);
+                    fence_proxy_async();
+                    mbar_arrive(pds_full);
                 }
             }
-            if (step_n > 0) {
-                mbar_wait(p_free, (step_n - 1) & 1);
-                mbar_wait(ds_free, (step_n - 1) & 1);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t off = (uint32_t)((q ^ (row & 7)) << 4);
-                sts128(sP + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                sts128(sDS + off, ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
-            }
-            fence_proxy_async();
-            mbar_arrive(pds_full);
-            ++step_n;
-            c = nx;
-            rd = rd_next;
         }
-    } else {
-        // ===================== drain warps: dQ tiles and, per item, dK / dV leave straight from registers ================
-        reg_dealloc<112>();
+    } else if (warp >= 12) {
+        // ===================== drain warps: dQ tiles -> TMA fp32 reduce-add; dK / dV -> bf16 TMA store ================
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
         const uint32_t t_dq = tmem_base + lane_off + T_DQ;
+        uint8_t* stg = smem + B_OFF_STG;
+        const uint32_t stg_row = smem_u32(stg) + row * 128;
         uint32_t item_n = 0, step_n = 0;
-        Cursor<KIND> c;
-        c.init(p);
-        while (c.valid) {
-            const int b = c.b, g = c.g, kt = c.kt;
-            bool moved = false;
-            while (!moved) {
-                const int qt = c.qt();
-                const int i = qt * BT + row;
-                const long long bh = (long long)b * p.n_q + 2 * g + c.hh;
-                const bool first = c.owned && kt == 0;
-                const bool last = c.owned && kt == c.last_kt(p, qt);
-                const uint32_t db = step_n & 1, du = step_n >> 1;
-                mbar_wait(&dq_full[db], du & 1);
-                tc_fence_after();
-                float* acc = p.dq_acc + (bh * p.Lp + i) * D;
-                bf16* out = p.dq + ((long long)b * p.L + i) * p.ld_d + (2 * g + c.hh) * D;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask;
+            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            for (int hh = 0; hh < 2; ++hh) {
+                for (unsigned qm = qmask; qm; qm &= qm - 1, ++step_n) {
+                    const int qt = __ffs(qm) - 1;
+                    const uint32_t db = step_n & 1, du = step_n >> 1;
+                    mbar_wait(&dq_full[db], du & 1);
+                    tc_fence_after();
+                    float* dst = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t o[32];
-                    tmem_ld_32x32(t_dq + db * 64 + half * 32, o);
-                    tmem_ld_wait();
-                    if (half == 1) {
-                        tc_fence_before();
-                        mbar_arrive(&dq_free[db]);
-                    }
-                    float* a = acc + half * 32;
-                    if (last) {
-                        // every earlier contribution came from this thread: read the partial sum back (L2: the REDs
-                        // were performed there), add, convert, store the bf16 row
-                        if (i < p.L) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                float v[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * q + e]) * p.scale;
-                                if (!first) {
-                                    const float4 p0 = __ldcg(reinterpret_cast<const float4*>(a + 8 * q));
-                                    const float4 p1 = __ldcg(reinterpret_cast<const float4*>(a + 8 * q + 4));
-                                    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-                                    v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-                                }
-                                *reinterpret_cast<bf16x8*>(out + half * 32 + 8 * q) = float_to_bf16x8(v);
-                            }
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(t_dq + db * 64 + half * 32, o);
+                        tmem_ld_wait();
+                        if (half == 1) {
+                            tc_fence_before();
+                            mbar_arrive(&dq_free[db]);
                         }
-                    } else if (first) {
+                        if (row == 0) bulk_wait_read0();  // the previous bulk op has finished reading the staging buffer
+                        named_bar_sync(3, 128);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            __stcg(reinterpret_cast<float4*>(a + 4 * q),
-                                   make_float4(__uint_as_float(o[4 * q]) * p.scale, __uint_as_float(o[4 * q + 1]) * p.scale,
-                                               __uint_as_float(o[4 * q + 2]) * p.scale, __uint_as_float(o[4 * q + 3]) * p.scale));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            red_add_v4(a + 4 * q, __uint_as_float(o[4 * q]) * p.scale, __uint_as_float(o[4 * q + 1]) * p.scale,
-                                       __uint_as_float(o[4 * q + 2]) * p.scale, __uint_as_float(o[4 * q + 3]) * p.scale);
+                        for (int ch = 0; ch < 8; ++ch)
+                            sts128(stg_row + ((ch ^ (row & 7)) << 4), __float_as_uint(__uint_as_float(o[4 * ch]) * p.scale),
+                                   __float_as_uint(__uint_as_float(o[4 * ch + 1]) * p.scale),
+                                   __float_as_uint(__uint_as_float(o[4 * ch + 2]) * p.scale),
+                                   __float_as_uint(__uint_as_float(o[4 * ch + 3]) * p.scale));
+                        fence_proxy_async();
+                        named_bar_sync(3, 128);
+                        if (row == 0) {
+                            bulk_reduce_add_f32(dst + half * (DQ_TILE_FLOATS / 2), stg, DQ_TILE_FLOATS * 2);
+                            bulk_commit();
+                        }
                     }
                 }
-                ++step_n;
-                moved = c.advance(p);
             }
-            // ---- item epilogue: dK then dV -> bf16 rows (keys past L are not written)
+            // ---- item epilogue: dK then dV -> bf16 -> staging -> TMA store (rows past L are clipped)
             mbar_wait(dkv_full, item_n & 1);
             tc_fence_after();
-            const int j = kt * BT + row;
 #pragma unroll 1
             for (int which = 0; which < 2; ++which) {
                 const uint32_t t_acc = tmem_base + lane_off + (which == 0 ? T_DK : T_DV);
                 const float mul = (which == 0) ? p.scale : 1.f;
-                bf16* dst = (which == 0 ? p.dk : p.dv) + ((long long)b * p.L + j) * p.ld_d + g * D;
+                uint32_t pk[32];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t o[32];
                     tmem_ld_32x32(t_acc + half * 32, o);
                     tmem_ld_wait();
-                    if (which == 1 && half == 1) {
-                        tc_fence_before();
-                        mbar_arrive(dkv_free);
-                    }
-                    if (j < p.L) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float v[8];
+                    for (int k = 0; k < 16; ++k)
+                        pk[half * 16 + k] = pack_bf16(__uint_as_float(o[2 * k]) * mul, __uint_as_float(o[2 * k + 1]) * mul);
+                }
+                if (which == 1) {
+                    tc_fence_before();
+                    mbar_arrive(dkv_free);
+                }
+                if (row == 0) bulk_wait_read0();
+                named_bar_sync(3, 128);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * q + e]) * mul;
-                            *reinterpret_cast<bf16x8*>(dst + half * 32 + 8 * q) = float_to_bf16x8(v);
-                        }
-                    }
+                for (int ch = 0; ch < 8; ++ch)
+                    sts128(stg_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                fence_proxy_async();
+                named_bar_sync(3, 128);
+                if (row == 0) {
+                    tma_store_3d(which == 0 ? &tmdK : &tmdV, stg, g * D, kt * BT, b);
+                    bulk_commit();
                 }
             }
-            ++item_n;
         }
+        if (row == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -1189,19 +1176,22 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
     }
 }
 
-// dQ of the groups that were split over several CTAs: dq_acc [bh][Lp][64] fp32 -> dq bf16 [B*L, ld_d] + h*64, heads
-// [bh0, B * n_q).  One thread per 8 consecutive head-dim elements.
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, int bh0, int B, int L, int Lp, int n_q,
+// dq_acc (tile-major, swizzled fp32) -> dq bf16 [B*L, ld_d] + h*64.  One thread per 8 consecutive head-dim elements.
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, int B, int L, int n_q, int q_tiles,
                                        bf16* __restrict__ dq, long long ld_d) {
-    const long long total = (long long)(B * n_q - bh0) * L * 8;
+    const long long total = (long long)B * n_q * L * 8;
     for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(x & 7);
         long long r = x >> 3;
-        const int i = (int)(r % L);
-        const int bh = bh0 + (int)(r / L);
-        const int b = bh / n_q, h = bh - b * n_q;
-        const float* src = acc + ((long long)bh * Lp + i) * D + c8 * 8;
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+        const int h = (int)(r % n_q);
+        r /= n_q;
+        const int i = (int)(r % L), b = (int)(r / L);
+        const int qt = i >> 7, row = i & 127;
+        const float* tile = acc + (((long long)b * n_q + h) * q_tiles + qt) * DQ_TILE_FLOATS + (c8 >> 2) * (DQ_TILE_FLOATS / 2) +
+                            row * 32;
+        const int ch = (c8 & 3) * 2;
+        const float4 v0 = *reinterpret_cast<const float4*>(tile + ((ch ^ (row & 7)) << 2));
+        const float4 v1 = *reinterpret_cast<const float4*>(tile + (((ch + 1) ^ (row & 7)) << 2));
         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         *reinterpret_cast<bf16x8*>(dq + ((long long)b * L + i) * ld_d + h * D + c8 * 8) = float_to_bf16x8(f);
     }
@@ -1304,22 +1294,31 @@ int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
 
 template <int KIND, bool DROP>
 int launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                 const BwdParams& p, int grid, cudaStream_t stream) {
+                 const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
     static PerDeviceOnce cfg;
     if (cfg.need())
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<KIND, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    attn_bwd_kernel<KIND, DROP><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    const int sms = sm_count();
+    const int grid = p.total < sms ? p.total : sms;
+    attn_bwd_kernel<KIND, DROP><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
 template <int KIND>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-               const BwdParams& p, int grid, cudaStream_t stream) {
-    return p.drop_on ? launch_bwd_t<KIND, true>(tq, tk, tv, tdo, p, grid, stream)
-                     : launch_bwd_t<KIND, false>(tq, tk, tv, tdo, p, grid, stream);
+               const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdParams& p, cudaStream_t stream) {
+    return p.drop_on ? launch_bwd_t<KIND, true>(tq, tk, tv, tdo, tdk, tdv, p, stream)
+                     : launch_bwd_t<KIND, false>(tq, tk, tv, tdo, tdk, tdv, p, stream);
 }
 
 }  // namespace
+
+// debug hook: subsequent launches record a timeline of CTA 0 into buf (4 roles x cap x (tag, clock) int64 pairs)
+extern "C" int gamer_attn_set_trace(void* buf, int cap) {
+    g_trace.buf = reinterpret_cast<long long*>(buf);
+    g_trace.cap = cap;
+    return 0;
+}
 
 bool attn_tc_supported(int L, int n_q, int n_kv, int head_dim) {
     return head_dim == D && n_kv > 0 && n_q == 2 * n_kv && L >= 1 && (L + BT - 1) / BT <= 32;
@@ -1351,6 +1350,7 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, long long ld, int B
     p.act = act; p.sess = sess; p.scale_log2 = scale * 1.4426950408889634f; p.vmean = vmean; p.lse = lse;
     p.keep = reinterpret_cast<uint32_t*>(keep);
     p.drop = make_drop(drop, 8);
+    p.tr = g_trace;
     GAMER_REQUIRE(p.drop.thresh == 0 || keep != nullptr,
                   "attention dropout needs the keep-word buffer (gamer_attn_keep_bytes) the backward reads back");
     switch (kind) {
@@ -1372,7 +1372,7 @@ static BwdLayout bwd_layout(int B, int L, int n_q) {
     bl.off_lse = bl.off_dsum + align256((long long)B * n_q * bl.ml.Lp * 4);
     bl.off_uni = bl.off_lse + align256((long long)B * n_q * bl.ml.Lp * 4);
     bl.off_acc = bl.off_uni + align256((long long)B * 4);
-    bl.acc_bytes = (long long)B * n_q * bl.ml.Lp * D * 4;
+    bl.acc_bytes = (long long)B * n_q * bl.ml.k_tiles * DQ_TILE_FLOATS * 4;
     bl.bytes = bl.off_acc + align256(bl.acc_bytes);
     return bl;
 }
@@ -1392,37 +1392,26 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     float* acc = reinterpret_cast<float*>(w8 + bl.off_acc);
     const DropParams dp = make_drop(drop, 8);
     GAMER_REQUIRE(dp.thresh == 0 || keep != nullptr, "attention dropout: the backward needs the forward's keep words");
-    GAMER_REQUIRE((reinterpret_cast<uintptr_t>(dq) & 15) == 0 && (reinterpret_cast<uintptr_t>(dk) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(dv) & 15) == 0 && (ld_d * 2) % 16 == 0,
-                  "attention gradients must be 16-byte aligned (ld=%lld)", ld_d);
-    // Work split (Cursor): groups dealt in full rounds are owned by one CTA and need neither a zeroed accumulator nor the
-    // convert pass; the remaining n_groups mod grid groups do.
-    const int total = B * n_kv * bl.ml.k_tiles;
-    const int sms = sm_count();
-    const int grid = total < sms ? total : sms;
-    const int n_groups = B * n_kv;
-    const int full = (n_groups / grid) * grid;
-    const int bh0 = 2 * full;                                  // first (sequence, head) of the split groups
-    const long long per_bh = (long long)bl.ml.Lp * D;         // floats per (sequence, head) in the accumulator
-    GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)B * 4, stream));
-    if (bh0 < B * n_q)
-        GAMER_CHECK_CUDA(cudaMemsetAsync(acc + bh0 * per_bh, 0, (size_t)(B * n_q - bh0) * per_bh * 4, stream));
+    // uni bits and the dQ accumulator are adjacent: one memset
+    GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)(bl.off_acc - bl.off_uni) + (size_t)bl.acc_bytes, stream));
     {
         const float keep_prob = 1.0f / dp.scale;
-        const dim3 pgrid((bl.ml.Lp * n_q * 8 + 255) / 256, B);
-        attn_bwd_prep_kernel<<<pgrid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o),
-                                                        ld_o, B, L, bl.ml.Lp, n_q, lse, keep_prob, log2f(keep_prob), dsum,
-                                                        lse_p, uni);
+        const dim3 grid((bl.ml.Lp * n_q * 8 + 255) / 256, B);
+        attn_bwd_prep_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o),
+                                                       ld_o, B, L, bl.ml.Lp, n_q, lse, keep_prob, log2f(keep_prob), dsum,
+                                                       lse_p, uni);
         GAMER_LAUNCH_CHECK();
     }
-    CUtensorMap tq, tk, tv, tdo;
+    CUtensorMap tq, tk, tv, tdo, tdk, tdv;
     if (int e = make_tmap_seq(&tq, q, B, L, n_q * D, ld)) return e;
     if (int e = make_tmap_seq(&tk, k, B, L, n_kv * D, ld)) return e;
     if (int e = make_tmap_seq(&tv, v, B, L, n_kv * D, ld)) return e;
     if (int e = make_tmap_seq(&tdo, d_o, B, L, n_q * D, ld_o)) return e;
+    if (int e = make_tmap_seq(&tdk, dk, B, L, n_kv * D, ld_d)) return e;
+    if (int e = make_tmap_seq(&tdv, dv, B, L, n_kv * D, ld_d)) return e;
     BwdParams p{};
     p.B = B; p.L = L; p.Lp = bl.ml.Lp; p.n_q = n_q; p.n_kv = n_kv; p.P = P;
-    p.q_tiles = bl.ml.k_tiles; p.k_tiles = bl.ml.k_tiles; p.total = total;
+    p.q_tiles = bl.ml.k_tiles; p.k_tiles = bl.ml.k_tiles; p.total = B * n_kv * bl.ml.k_tiles;
     p.ka = reinterpret_cast<const int*>(w8 + bl.ml.off_ka);
     p.ks = reinterpret_cast<const int*>(w8 + bl.ml.off_ks);
     p.blk = reinterpret_cast<const int4*>(w8 + bl.ml.off_blk);
@@ -1431,22 +1420,21 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     p.lse_p = lse_p; p.dsum_p = dsum; p.uni_bits = uni;
     p.keep = reinterpret_cast<const uint32_t*>(keep);
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.inv_L = 1.0f / (float)L; p.dq_acc = acc;
-    p.dq = reinterpret_cast<bf16*>(dq); p.dk = reinterpret_cast<bf16*>(dk); p.dv = reinterpret_cast<bf16*>(dv);
-    p.ld_d = ld_d;
     p.drop_on = dp.thresh != 0;
+    p.tr = g_trace;
     int e;
     switch (kind) {
-        case 0: e = launch_bwd<0>(tq, tk, tv, tdo, p, grid, stream); break;
-        case 1: e = launch_bwd<1>(tq, tk, tv, tdo, p, grid, stream); break;
-        case 2: e = launch_bwd<2>(tq, tk, tv, tdo, p, grid, stream); break;
-        default: e = launch_bwd<3>(tq, tk, tv, tdo, p, grid, stream); break;
+        case 0: e = launch_bwd<0>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        case 1: e = launch_bwd<1>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        case 2: e = launch_bwd<2>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
+        default: e = launch_bwd<3>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
     }
     if (e) return e;
-    if (bh0 < B * n_q) {
-        const long long n = (long long)(B * n_q - bh0) * L * 8;
-        const long long blocks = (n + 255) / 256;
+    {
+        const long long total = (long long)B * n_q * L * 8;
+        const long long blocks = (total + 255) / 256;
         attn_dq_convert_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
-            acc, bh0, B, L, bl.ml.Lp, n_q, reinterpret_cast<bf16*>(dq), ld_d);
+            acc, B, L, n_q, bl.ml.k_tiles, reinterpret_cast<bf16*>(dq), ld_d);
         GAMER_LAUNCH_CHECK();
     }
     return 0;

@@ -25,7 +25,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
+        : "r"(addr), "r"(parity), "r"(0x10000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     return done != 0;
 }
@@ -33,7 +33,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 22); ++it)
+    for (uint32_t it = 0; it < (1u << 18); ++it)
         if (mbar_try_wait(addr, parity)) return;
     mbar_timeout();
 }
@@ -174,6 +174,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r)
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -108,6 +108,8 @@ long long gamer_attn_workspace_bytes(int B, int L, int n_q, int n_kv);
  * 32 keys) into `keep` (gamer_attn_keep_bytes bytes; may be NULL when drop is NULL or drop->p == 0) and the backward of the
  * same call site reads it back, instead of regenerating the random stream. */
 long long gamer_attn_keep_bytes(int B, int L, int n_q);
+/* debug hook (tools/attn_trace.py): record an in-kernel timeline of CTA 0 of the next attention launches; buf = NULL disables */
+int gamer_attn_set_trace(void* buf, int cap);
 int gamer_attn_fwd(const void* q, const void* k, const void* v, long long ld, int B, int L, int n_q, int n_kv,
                    int head_dim, int mask_kind, int tokens_per_item, const int* am, const int* act, const int* sess,
                    float scale, void* workspace, void* o, long long ld_o, float* lse, const gamer_dropout_t* drop,
