@@ -701,35 +701,39 @@ struct BwdParams {
     const uint32_t* keep;      // the forward's keep words
     float scale, scale_log2, inv_L;
     float* dq_acc;       // [B, n_q, q_tiles][2 halves][128 rows][32 floats], 16-byte chunks XOR-swizzled by (row & 7)
+    bf16* dq;            // [B * L, ld_d]: head h at columns [64 h, 64 h + 64)
+    long long ld_d;
     int drop_on;
     Trace tr;
 };
 
 template <int KIND>
-__device__ __forceinline__ void bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask) {
-    // Work order.  A "group" = (sequence, kv head); its k_tiles items share Q / dO tiles and dQ accumulator tiles.
-    //  * full rounds: groups are dealt one per CTA and a CTA walks ITS group's key tiles 0..k_tiles-1 back to back (w
-    //    advances by gridDim.x between its items): every CTA carries the same load, and the group's tiles stay in L2;
-    //  * the last (n_groups mod gridDim.x) groups are dealt key-tile-major over all CTAs, heaviest key tile first (tile 0
-    //    meets the most query tiles), so the tail of the launch is made of the light items.
+__device__ __forceinline__ bool bwd_decode(int w, const BwdParams& p, int& b, int& g, int& kt, unsigned& qmask,
+                                           unsigned& lastmask) {
+    // Work order.  A "group" = (sequence, kv head) is OWNED by one CTA, which walks the group's key tiles 0..k_tiles-1 back
+    // to back (w = blockIdx.x + m * gridDim.x  <->  group blockIdx.x + (m / k_tiles) * gridDim.x, key tile m % k_tiles).
+    // The group's Q / dO tiles stay in L2 across its key tiles, and because every contribution to a dQ tile comes from
+    // the same CTA in key-tile order the fp32 dQ accumulator needs neither a zero fill nor a conversion pass: the first
+    // contribution (key tile 0) is a plain store, the middle ones are reduce-adds, and the last one (lastmask) reads the
+    // running sum back, adds its own tile and writes bf16 dQ.
     const int grid = (int)gridDim.x;
-    const int n_groups = p.B * p.n_kv;
-    const int full = (n_groups / grid) * grid;
-    int grp;
-    if (w < full * p.k_tiles) {
-        const int r = w % (grid * p.k_tiles);
-        kt = r / grid;
-        grp = (w / (grid * p.k_tiles)) * grid + r % grid;
-    } else {
-        const int wr = w - full * p.k_tiles, rem = n_groups - full;
-        kt = wr / rem;
-        grp = full + wr % rem;
-    }
+    const int m = w / grid;
+    kt = m % p.k_tiles;
+    const int grp = (m / p.k_tiles) * grid + w % grid;
+    if (grp >= p.B * p.n_kv) return false;
     b = grp / p.n_kv;
     g = grp % p.n_kv;
     const unsigned all = (p.q_tiles >= 32) ? 0xffffffffu : ((1u << p.q_tiles) - 1u);
-    if (kind_causal<KIND>()) qmask = ((all >> kt) << kt) | (p.uni_bits[b] & all);
-    else qmask = all;
+    if (kind_causal<KIND>()) {
+        // query tile qt meets key tile kt when qt >= kt, or always when it holds a uniform row (P = 1/L on every key)
+        const unsigned uni = p.uni_bits[b] & all;
+        qmask = ((all >> kt) << kt) | uni;
+        lastmask = (kt == p.k_tiles - 1) ? (uni | (1u << kt)) : ((1u << kt) & ~uni);
+    } else {
+        qmask = all;
+        lastmask = (kt == p.k_tiles - 1) ? all : 0u;
+    }
+    return true;
 }
 
 // One 32-key block of a backward step, for one query row.  In: s = scores (raw words), dp = dO V^T.  Out: pk = the dV
@@ -817,9 +821,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* dkv_full = bars + 19;
     uint64_t* dkv_free = bars + 20;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint32_t* conv_flag = reinterpret_cast<uint32_t*>(bars + 22);   // items whose dQ accumulator writes have landed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        *conv_flag = 0u;
         prefetch_tmap(&tmQ);
         prefetch_tmap(&tmK);
         prefetch_tmap(&tmV);
@@ -860,8 +866,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t item_n = 0, step_n = 0;
             for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
                 int b, g, kt;
-                unsigned qmask;
-                bwd_decode<KIND>(w, p, b, g, kt, qmask);
+                unsigned qmask, lastmask;
+                if (!bwd_decode<KIND>(w, p, b, g, kt, qmask, lastmask)) break;
                 const int ks = item_n & 1;
                 uint8_t* skv = smem + B_OFF_KV + ks * B_KV_STAGE;
                 mbar_wait(&kv_free[ks], ((item_n >> 1) & 1) ^ 1);
@@ -899,10 +905,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ===================== MMA issuer (converged warp, elected lane issues) =====================
         uint32_t item_n = 0, step_n = 0;
         const uint32_t sp = smem_u32(smem + B_OFF_P), sds = smem_u32(smem + B_OFF_DS);
+        Trace tr = p.tr;
+        if (blockIdx.x != 0 || lane != 0) tr.buf = nullptr;
+        int tn = 0;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
             int b, g, kt;
-            unsigned qmask;
-            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            unsigned qmask, lastmask;
+            if (!bwd_decode<KIND>(w, p, b, g, kt, qmask, lastmask)) break;
             const int N = 2 * __popc(qmask);
             const int ks = item_n & 1;
             const uint32_t sk = smem_u32(smem + B_OFF_KV + ks * B_KV_STAGE), sv = sk + TILE_BYTES;
@@ -923,16 +932,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int st = step_n & 1;
                 const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
                 const uint32_t sqn = smem_u32(smem + B_OFF_QDO + (st ^ 1) * B_QDO_STAGE);
+                trace_pt(tr, 0, tn, 1);
                 if (n + 1 < N) {
                     mbar_wait(&qdo_full[st ^ 1], ((step_n + 1) >> 1) & 1);
                     mbar_wait(s_free, step_n & 1);
+                    trace_pt(tr, 0, tn, 2);
                     tc_fence_after();
                     issue_nt_128x128x64(tmem_base + T_S, sqn, sk, s_full);                   // S(n+1) = Q K^T
                     mbar_wait(dp_free, step_n & 1);
                     tc_fence_after();
                     issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv, dp_full);    // dP(n+1) = dO V^T
                 }
+                trace_pt(tr, 0, tn, 3);
                 mbar_wait(pds_full, step_n & 1);
+                trace_pt(tr, 0, tn, 4);
                 if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
                 tc_fence_after();
                 issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0, p_free);   // dV += P^T dO
@@ -944,8 +957,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tc_fence_after();
                 }
                 const bool last = n + 1 == N;
+                trace_pt(tr, 0, tn, 5);
                 issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false, &dq_full[db], ds_free,   // dQ = dS K
                                     last ? dkv_full : nullptr, last ? &kv_free[ks] : nullptr);
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== converter warps: finished dQ tiles, fp32 running sum (L2) -> bf16 rows =====================
+        // Runs one item behind the drain warps, off every critical path: the drain thread publishes the number of items
+        // whose accumulator writes have landed; a tile is converted by the item that made its last contribution.
+        const int t = (int)threadIdx.x - 64;
+        uint32_t item_n = 0;
+        Trace tr = p.tr;
+        if (blockIdx.x != 0 || t != 0) tr.buf = nullptr;
+        int tn = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
+            int b, g, kt;
+            unsigned qmask, lastmask;
+            if (!bwd_decode<KIND>(w, p, b, g, kt, qmask, lastmask)) break;
+            if (lastmask == 0u) continue;
+            trace_pt(tr, 2, tn, 40);
+            while (*reinterpret_cast<volatile uint32_t*>(conv_flag) < item_n + 1) __nanosleep(256);
+            __threadfence_block();
+            trace_pt(tr, 2, tn, 41);
+            for (int hh = 0; hh < 2; ++hh) {
+                for (unsigned qm = lastmask; qm; qm &= qm - 1) {
+                    const int qt = __ffs(qm) - 1;
+                    const float* tile = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
+                    bf16* out = p.dq + ((long long)b * p.L + qt * BT) * p.ld_d + (2 * g + hh) * D;
+                    const int rows = min(BT, p.L - qt * BT);
+                    // two batches of eight 32-byte chunks per thread: all loads of a batch in flight before the first store
+                    // (the compiler cannot hoist loads over the stores on its own: the pointers may alias)
+#pragma unroll 1
+                    for (int it0 = 0; it0 < 16; it0 += 8) {
+                        float4 v[8][2];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int id = (it0 + j) * 64 + t, r = id >> 3, c8 = id & 7;   // 8 threads per 128-byte output row
+                            const float* src = tile + (c8 >> 2) * (DQ_TILE_FLOATS / 2) + r * 32;
+                            const int ch = (c8 & 3) * 2;
+                            if (r < rows) {
+                                v[j][0] = __ldcg(reinterpret_cast<const float4*>(src + ((ch ^ (r & 7)) << 2)));
+                                v[j][1] = __ldcg(reinterpret_cast<const float4*>(src + (((ch + 1) ^ (r & 7)) << 2)));
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int id = (it0 + j) * 64 + t, r = id >> 3, c8 = id & 7;
+                            if (r < rows) {
+                                const float f[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w,
+                                                    v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+                                *reinterpret_cast<bf16x8*>(out + (long long)r * p.ld_d + c8 * 8) = float_to_bf16x8(f);
+                            }
+                        }
+                    }
+                }
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -961,10 +1027,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t sP = smem_u32(smem + B_OFF_P + wgi * TILE_BYTES) + row * 128;
         const uint32_t sDS = smem_u32(smem + B_OFF_DS + wgi * TILE_BYTES) + row * 128;
         uint32_t item_n = 0, step_n = 0;
+        Trace tr = p.tr;
+        if (blockIdx.x != 0 || lane != 0 || wq != 0 || wgi != 0) tr.buf = nullptr;
+        int tn = 0;
+        const int trole = 1 + wgi;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
             int b, g, kt;
-            unsigned qmask;
-            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            unsigned qmask, lastmask;
+            if (!bwd_decode<KIND>(w, p, b, g, kt, qmask, lastmask)) break;
             const int ks = item_n & 1;
             mbar_wait(&kv_full[ks], (item_n >> 1) & 1);  // key codes
             const uint8_t* meta = smem + B_OFF_KV + ks * B_KV_STAGE + 2 * TILE_BYTES;
@@ -978,6 +1048,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const int i = qt * BT + row;
                     // per-row scalars travel with the Q / dO stage (padded copies: lse' = +inf, dsum' = 0 past L)
                     const int st = step_n & 1;
+                    trace_pt(tr, trole, tn, 10);
                     mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
                     const float* rowf = reinterpret_cast<const float*>(smem + B_OFF_QDO + st * B_QDO_STAGE + 2 * TILE_BYTES);
                     const float lse_i = rowf[row], dsum_i = rowf[128 + row];
@@ -991,9 +1062,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const float pu = uni ? p.inv_L : 0.f;
                     const float neg_lse = -lse_i;       // -inf on uniform / padding rows: exp2 -> 0
                     const float neg_dsum = -dsum_i;
+                    trace_pt(tr, trole, tn, 11);
                     mbar_wait(s_full, step_n & 1);
                     mbar_wait(dp_full, step_n & 1);
                     tc_fence_after();
+                    trace_pt(tr, trole, tn, 12);
 #pragma unroll 1
                     for (int bk = 0; bk < 2; ++bk) {
                         const int j0 = jbase + bk * 32;
@@ -1014,6 +1087,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             tmem_ld_32x32(t_s + bk * 32, s);
                             tmem_ld_32x32(t_dp + bk * 32, dp);
                             tmem_ld_wait();
+                            trace_pt(tr, trole, tn, 13);
                             if (bk == 1) {
                                 tc_fence_before();
                                 mbar_arrive(s_free);
@@ -1032,10 +1106,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 bwd_block<KIND, DROP, BLK_MASK_DIAG>(s, dp, pk, ds, ka + bk * 128, kss + bk * 128, act_i, sess_i, j0,
                                                                      i, istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
                         }
+                        trace_pt(tr, trole, tn, 14);
                         if (bk == 0 && step_n > 0) {
                             mbar_wait(p_free, (step_n - 1) & 1);
                             mbar_wait(ds_free, (step_n - 1) & 1);
                         }
+                        trace_pt(tr, trole, tn, 15);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t off = (uint32_t)(((bk * 4 + q) ^ (row & 7)) << 4);
@@ -1045,6 +1121,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                     fence_proxy_async();
                     mbar_arrive(pds_full);
+                    trace_pt(tr, trole, tn, 16);
                 }
             }
         }
@@ -1057,17 +1134,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint8_t* stg = smem + B_OFF_STG;
         const uint32_t stg_row = smem_u32(stg) + row * 128;
         uint32_t item_n = 0, step_n = 0;
+        Trace tr = p.tr;
+        if (blockIdx.x != 0 || row != 0) tr.buf = nullptr;
+        int tn = 0;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++item_n) {
             int b, g, kt;
-            unsigned qmask;
-            bwd_decode<KIND>(w, p, b, g, kt, qmask);
+            unsigned qmask, lastmask;
+            if (!bwd_decode<KIND>(w, p, b, g, kt, qmask, lastmask)) break;
             for (int hh = 0; hh < 2; ++hh) {
                 for (unsigned qm = qmask; qm; qm &= qm - 1, ++step_n) {
                     const int qt = __ffs(qm) - 1;
                     const uint32_t db = step_n & 1, du = step_n >> 1;
-                    mbar_wait(&dq_full[db], du & 1);
-                    tc_fence_after();
+                    trace_pt(tr, 3, tn, 30);
                     float* dst = p.dq_acc + (((long long)b * p.n_q + 2 * g + hh) * p.q_tiles + qt) * DQ_TILE_FLOATS;
+                    const bool first = kt == 0;
+                    mbar_wait(&dq_full[db], du & 1);
+                    trace_pt(tr, 3, tn, 31);
+                    tc_fence_after();
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
                         uint32_t o[32];
@@ -1088,10 +1171,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         fence_proxy_async();
                         named_bar_sync(3, 128);
                         if (row == 0) {
-                            bulk_reduce_add_f32(dst + half * (DQ_TILE_FLOATS / 2), stg, DQ_TILE_FLOATS * 2);
+                            // key tile 0 opens the running sum with a plain store (no zero fill of the accumulator)
+                            if (first) bulk_store_1d(dst + half * (DQ_TILE_FLOATS / 2), stg, DQ_TILE_FLOATS * 2);
+                            else bulk_reduce_add_f32(dst + half * (DQ_TILE_FLOATS / 2), stg, DQ_TILE_FLOATS * 2);
                             bulk_commit();
                         }
                     }
+                    trace_pt(tr, 3, tn, 32);
                 }
             }
             // ---- item epilogue: dK then dV -> bf16 -> staging -> TMA store (rows past L are clipped)
@@ -1127,8 +1213,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     bulk_commit();
                 }
             }
+            // The item's dQ stores / reduce-adds (every bulk group but the two stores just committed) must have landed before
+            // the next key tile of the group adds to the same accumulator tiles, and before the converter warps read the
+            // tiles this item completed.
+            if (row == 0) {
+                bulk_wait_group2();
+                fence_proxy_async_all();
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t*>(conv_flag) = item_n + 1;
+            }
         }
-        if (row == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -1173,27 +1267,6 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
         }
         dsum_p[pi] = real ? s : 0.f;
         lse_p[pi] = ls;
-    }
-}
-
-// dq_acc (tile-major, swizzled fp32) -> dq bf16 [B*L, ld_d] + h*64.  One thread per 8 consecutive head-dim elements.
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, int B, int L, int n_q, int q_tiles,
-                                       bf16* __restrict__ dq, long long ld_d) {
-    const long long total = (long long)B * n_q * L * 8;
-    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(x & 7);
-        long long r = x >> 3;
-        const int h = (int)(r % n_q);
-        r /= n_q;
-        const int i = (int)(r % L), b = (int)(r / L);
-        const int qt = i >> 7, row = i & 127;
-        const float* tile = acc + (((long long)b * n_q + h) * q_tiles + qt) * DQ_TILE_FLOATS + (c8 >> 2) * (DQ_TILE_FLOATS / 2) +
-                            row * 32;
-        const int ch = (c8 & 3) * 2;
-        const float4 v0 = *reinterpret_cast<const float4*>(tile + ((ch ^ (row & 7)) << 2));
-        const float4 v1 = *reinterpret_cast<const float4*>(tile + (((ch + 1) ^ (row & 7)) << 2));
-        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        *reinterpret_cast<bf16x8*>(dq + ((long long)b * L + i) * ld_d + h * D + c8 * 8) = float_to_bf16x8(f);
     }
 }
 
@@ -1299,8 +1372,11 @@ int launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     if (cfg.need())
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<KIND, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     const int sms = sm_count();
-    const int grid = p.total < sms ? p.total : sms;
-    attn_bwd_kernel<KIND, DROP><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
+    const int n_groups = p.B * p.n_kv;
+    const int grid = n_groups < sms ? n_groups : sms;
+    BwdParams pp = p;
+    pp.total = (n_groups + grid - 1) / grid * grid * p.k_tiles;   // walk index bound: every CTA runs the same number of rounds
+    attn_bwd_kernel<KIND, DROP><<<grid, B_THREADS, B_SMEM, stream>>>(tq, tk, tv, tdo, tdk, tdv, pp);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
@@ -1392,8 +1468,8 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     float* acc = reinterpret_cast<float*>(w8 + bl.off_acc);
     const DropParams dp = make_drop(drop, 8);
     GAMER_REQUIRE(dp.thresh == 0 || keep != nullptr, "attention dropout: the backward needs the forward's keep words");
-    // uni bits and the dQ accumulator are adjacent: one memset
-    GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)(bl.off_acc - bl.off_uni) + (size_t)bl.acc_bytes, stream));
+    // (the dQ accumulator needs no zero fill: the first contribution to a tile is a store)
+    GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)B * 4, stream));
     {
         const float keep_prob = 1.0f / dp.scale;
         const dim3 grid((bl.ml.Lp * n_q * 8 + 255) / 256, B);
@@ -1420,6 +1496,7 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     p.lse_p = lse_p; p.dsum_p = dsum; p.uni_bits = uni;
     p.keep = reinterpret_cast<const uint32_t*>(keep);
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.inv_L = 1.0f / (float)L; p.dq_acc = acc;
+    p.dq = reinterpret_cast<bf16*>(dq); p.ld_d = ld_d;
     p.drop_on = dp.thresh != 0;
     p.tr = g_trace;
     int e;
@@ -1430,12 +1507,5 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
         default: e = launch_bwd<3>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
     }
     if (e) return e;
-    {
-        const long long total = (long long)B * n_q * L * 8;
-        const long long blocks = (total + 255) / 256;
-        attn_dq_convert_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
-            acc, B, L, n_q, bl.ml.k_tiles, reinterpret_cast<bf16*>(dq), ld_d);
-        GAMER_LAUNCH_CHECK();
-    }
     return 0;
 }

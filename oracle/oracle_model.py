@@ -111,8 +111,8 @@ def allow_matrix(kind: int, am: torch.Tensor, actions: torch.Tensor | None, sess
                  P: int = 5) -> torch.Tensor:
     """bool [B,L,L]: True where query i may attend key j (full forward / prefill)."""
     B, L = am.shape
-    i = torch.arange(L).view(1, L, 1)
-    j = torch.arange(L).view(1, 1, L)
+    i = torch.arange(L, device=am.device).view(1, L, 1)
+    j = torch.arange(L, device=am.device).view(1, 1, L)
     key_ok = am.bool().view(B, 1, L)
     if kind == MASK_CAUSAL:
         allow = (j <= i).expand(B, L, L)
@@ -136,7 +136,7 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 def rope_cos_sin(spec: Spec, position_ids: torch.Tensor):
     """Qwen3RotaryEmbedding.forward: inv_freq_i = theta^(-2i/d); emb = cat(f, f). position_ids [B or 1, S]."""
     d = spec.head_dim
-    inv = 1.0 / (spec.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    inv = 1.0 / (spec.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32, device=position_ids.device) / d))
     f = position_ids.float().unsqueeze(-1) * inv                        # [b,S,d/2]
     emb = torch.cat([f, f], dim=-1)
     return emb.cos(), emb.sin()
@@ -149,6 +149,9 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return x * cos.unsqueeze(1) + rot * sin.unsqueeze(1)
 
 
+USE_SDPA = False     # bench.py's gpu_baseline switches the attention core to F.scaled_dot_product_attention
+
+
 def masked_attention(q, k, v, allow, scale, zp=None):
     """q [B,Hq,S,d], k/v [B,Hkv,T,d], allow bool [B,S,T].  Additive finfo(fp32).min mask then softmax, exactly
     what SDPA computes for the reference: a row with no allowed key is *uniform over all T keys* (quirk Q1).
@@ -159,6 +162,11 @@ def masked_attention(q, k, v, allow, scale, zp=None):
     k = k.repeat_interleave(g, dim=1)
     v = v.repeat_interleave(g, dim=1)
     bias = torch.where(allow, 0.0, torch.finfo(torch.float32).min).unsqueeze(1)
+    if USE_SDPA and zp is None:
+        # the reference's default branch (sdpa_attention_forward with the materialised additive mask,
+        # Qwen3Multi/model.py:123-143): used by bench.py's GPU baseline, which times stock PyTorch on the same device
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=bias.to(q.dtype).expand(-1, q.shape[1], -1, -1),
+                                              dropout_p=0.0, scale=scale)
     s = torch.matmul(q, k.transpose(-1, -2)) * scale + bias
     p = torch.softmax(s, dim=-1)
     if zp is not None:
@@ -286,7 +294,7 @@ def forward(spec: Spec, W: dict, input_ids, attention_mask, labels=None, session
     ignore_index=-100, mean — or sum / num_items_in_batch when given.
     """
     B, L = input_ids.shape
-    positions = torch.arange(L)
+    positions = torch.arange(L, device=input_ids.device)
     k_self, k_cross = mask_kinds(spec)
     self_allow = allow_matrix(k_self, attention_mask, actions, session_ids, spec.n_positions)
     cross_allow = allow_matrix(k_cross, attention_mask, actions, session_ids, spec.n_positions) \

@@ -33,6 +33,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=65536, help="tokens per call (batch = tokens // L)")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--his", type=int, nargs="*", default=[100, 200, 500], help="history lengths (L = 5 (his + 1))")
+    ap.add_argument("--kinds", type=int, nargs="*", default=[0, 1, 2, 3])
     a = ap.parse_args()
     dev = "cuda:0"
     try:
@@ -41,7 +43,7 @@ def main():
         peak = 1400.0
     nq, nkv, hd = 6, 3, 64
     g = torch.Generator().manual_seed(0)
-    for his in (100, 200, 500):
+    for his in a.his:
         L = 5 * (his + 1)
         B = max(1, a.tokens // L)
         am = torch.ones(B, L, dtype=torch.int32, device=dev)
@@ -50,7 +52,7 @@ def main():
         qkv = torch.randn(B * L, 768, device=dev).to(torch.bfloat16)
         d_o = torch.randn(B * L, nq * hd, device=dev).to(torch.bfloat16)
         dqkv = torch.empty_like(qkv)
-        for kind in (0, 1, 2, 3):
+        for kind in a.kinds:
             for p in (0.0, 0.2):
                 drop = K.Dropout(1234, 0, 8 + kind, p) if p > 0 else None
                 o, lse, _, keep = K.attn_fwd(qkv, B, L, nq, nkv, hd, kind, 5, am, act, sess, hd ** -0.5, drop=drop)
