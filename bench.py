@@ -39,7 +39,11 @@ def parse():
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from the host (A/B switch)")
     ap.add_argument("--no-eval", action="store_true", help="skip the secondary constrained-beam-search evaluation leg")
     ap.add_argument("--eval-users", type=int, default=256)
+    ap.add_argument("--eval-iters", type=int, default=5)
+    ap.add_argument("--cpu-eval-users", type=int, default=4, help="users of the bounded CPU sample of the evaluation leg")
     ap.add_argument("--cpu-sample", type=int, default=8, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-on-B200 baseline leg")
+    ap.add_argument("--gpu-baseline-rows", type=int, default=64, help="rows per step of the stock-PyTorch GPU baseline")
     return ap.parse_args()
 
 
@@ -96,50 +100,79 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_reference_step_fn(max_his_len, rows, seed=0):
+def cpu_reference_step_fn(max_his_len, rows, seed=0, device="cpu", autocast=False, sdpa=False):
     """The reference arm / cpu_baseline: the fp32 oracle port (oracle/oracle_model.py, validated against the reference's
-    own classes) doing forward + backward + AdamW on the host cores.  Returns (step_fn, rows)."""
+    own classes) doing forward + backward + AdamW on the host cores.  Returns (step_fn, rows).
+
+    With device="cuda" the same port is the `gpu_baseline` leg: stock PyTorch kernels on the same B200 (materialised
+    [B, L, L] masks, F.scaled_dot_product_attention, the per-expert gather loop) in fp32 or under bf16 autocast — what the
+    reference executes on a GPU (Qwen3Multi/model.py:123-143, 573-741; Qwen3Moe/FFN.py:53-72)."""
     import torch
     from gamer_b200 import synthetic as syn
     from oracle import oracle_model as om
     spec = om.Spec(temperature=0.7)
     torch.manual_seed(42)
-    shapes = {}
-    from gamer_b200 import engine as E
     from gamer_b200 import modeling
     cfg = model_config(max_his_len)
     m = modeling.Qwen3MultiWithTemperature(cfg)              # parameter container only (CPU): reference init N(0, 0.02)
-    W = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items() if k != "lm_head.weight"}
+    W = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in m.state_dict().items() if k != "lm_head.weight"}
     W["lm_head.weight"] = W["model.embed_tokens.weight"]
     params = [v for k, v in W.items() if k != "lm_head.weight"]
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.01)
     cat = syn.make_catalogue(50_000, 1234)
     batch = syn.make_train_batch(cat, rows, max_his_len=max_his_len, seed=seed, full_length=True)
+    batch = {k: v.to(device) for k, v in batch.items()}
 
     def step():
-        opt.zero_grad(set_to_none=True)
-        out = om.forward(spec, W, **batch)
-        out["loss"].backward()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
-        opt.step()
-        return float(out["loss"].detach())
+        om.USE_SDPA = sdpa
+        try:
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                out = om.forward(spec, W, **batch)
+            out["loss"].backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        finally:
+            om.USE_SDPA = False
+        return out["loss"].detach()
 
     return step, rows
 
 
-def eval_leg(args, dev, world, rank, barrier):
-    """Secondary metric of BASELINE.json (configs[2]): trie-constrained beam-search evaluation of Qwen3SessionMoe,
-    ShortVideoAD-shaped synthetic users, max_his_len=100 (prompt = 501 tokens, full length), global batch 256 users
-    sharded exactly over the ranks, 20 beams, 4 new tokens, 250k-item candidate trie.  Returns the `eval` object of the
-    JSON line: users/s with inputs resident in HBM and end to end from pinned host buffers (H2D of the prompts + D2H of the
-    decoded sequences and scores inside the timed region)."""
+def gpu_baseline_leg(args, dev):
+    """`gpu_baseline`: the stock-PyTorch path on the same B200, timed with CUDA events on a bounded
+    sample of the headline workload, in fp32 and under bf16 autocast.  A reported baseline like `cpu_baseline`: the only
+    other place bench.py executes oracle/ code, never on the product path."""
     import torch
-    import torch.distributed as dist
+    out = {"unit": "samples/s", "kind": "port",
+           "note": "oracle port on cuda: materialised [B,L,L] additive masks + F.scaled_dot_product_attention + per-expert "
+                   "gather loop (the reference's GPU code path), dropout-free (in the baseline's favour), torch AdamW"}
+    rows = args.gpu_baseline_rows
+    L = 5 * (args.max_his_len + 1)
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        try:
+            step, _ = cpu_reference_step_fn(args.max_his_len, rows, device=dev, autocast=ac, sdpa=True)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 3
+            e0.record()
+            for _ in range(n):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = {"value": rows * n / (e0.elapsed_time(e1) / 1e3), "last_loss": float(loss)}
+            del step
+        except Exception as e:  # noqa: BLE001 (an OOM of the baseline must not lose the bench line)
+            out[name] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:120]}"}
+        torch.cuda.empty_cache()
+    out["sample"] = f"{rows} full-length rows (L={L}) per step x 3 steps after 2 warm-ups: fwd+bwd+clip+AdamW"
+    return out
+
+
+def eval_config(max_his_len):
     from transformers.models.qwen3_moe import Qwen3MoeConfig
-    from gamer_b200 import modeling
-    from gamer_b200 import synthetic as syn
-    from gamer_b200.distributed import shard_range
-    from gamer_b200.trie import flat_from_array, prefix_allowed_tokens_fn_by_last_token
     cfg = Qwen3MoeConfig.from_pretrained(os.path.join(ROOT, "config", "s2s-models", "Qwen3SessionMoe"))
     cfg.vocab_size = 1041
     cfg.num_behavior = 3
@@ -147,26 +180,89 @@ def eval_leg(args, dev, world, rank, barrier):
     cfg.use_behavior_token = True
     cfg.num_positions = 5
     cfg.num_experts = 6
-    cfg.n_positions = args.max_his_len + 1
+    cfg.n_positions = max_his_len + 1
     cfg.use_user_token = False
-    cfg.model_max_length = max(1024, 5 * (args.max_his_len + 1))
+    cfg.model_max_length = max(1024, 5 * (max_his_len + 1))
+    return cfg
+
+
+EVAL_BEAMS = 20
+EVAL_TRIE_ITEMS = 250_000
+
+
+def cpu_eval_baseline(args, users):
+    """Eval half of the reference arm / cpu_baseline: the oracle port of the constrained beam search
+    (oracle/oracle_decode.py — HF `_beam_search` + the Python trie walk, as test_SMB_decoder.py:159-177 drives them) on
+    the host cores, on `users` users of the same workload (501-token prompts, 20 beams, 250k-item trie)."""
+    import torch
+    from gamer_b200 import modeling
+    from gamer_b200 import synthetic as syn
+    from oracle import oracle_decode as od
+    from oracle import oracle_model as om
+    cfg = eval_config(args.max_his_len)
+    torch.manual_seed(43)
+    m = modeling.Qwen3SessionMoeWithTemperature(cfg)
+    spec = om.Spec.from_hf_config(cfg, "Qwen3SessionMoe", temperature=1.0)
+    W = {k: v.detach().float() for k, v in m.state_dict().items()}
+    W["lm_head.weight"] = W["model.embed_tokens.weight"]
+    cat = syn.make_catalogue(EVAL_TRIE_ITEMS, 1234)
+    items = cat.item_sequences(2)
+    tree = od.PrefixTree(items.tolist())
+    last = set(int(t) for t in items[:, -1]) | {syn.PAD}
+    batch, _ = syn.make_eval_batch(cat, users, max_his_len=args.max_his_len, target_behavior=2, seed=77, full_length=True)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        od.constrained_beam_search(spec, W, tree, last, batch["input_ids"], batch["attention_mask"],
+                                   batch.get("session_ids"), batch.get("extended_session_ids"), batch.get("actions"),
+                                   num_beams=EVAL_BEAMS, max_new_tokens=4)
+    dt = time.perf_counter() - t0
+    return {"value": users / dt, "unit": "users/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{users} users x {EVAL_BEAMS} beams, 501-token prompts, 4 new tokens, {EVAL_TRIE_ITEMS // 1000}k-item trie: "
+                      f"oracle port of HF beam search + Python trie (fp32), one call"}
+
+
+def eval_leg(args, dev, world, rank, barrier):
+    """Secondary metric of BASELINE.json (configs[2]): trie-constrained beam-search evaluation of Qwen3SessionMoe,
+    ShortVideoAD-shaped synthetic users, max_his_len=100 (prompt = 501 tokens, full length), global batch 256 users
+    sharded exactly over the ranks, 20 beams, 4 new tokens, 250k-item candidate trie.  Returns the `eval` object of the
+    JSON line: users/s with inputs resident in HBM and end to end from pinned host buffers (H2D of the prompts + D2H of the
+    decoded item tuples and scores inside the timed region), its own roofline (dominant kernel of one profiled call) and,
+    at N=1, the CPU baseline of the same call."""
+    import torch
+    import torch.distributed as dist
+    from gamer_b200 import _cabi, modeling
+    from gamer_b200 import synthetic as syn
+    from gamer_b200.distributed import shard_range
+    from gamer_b200.trie import flat_from_array, prefix_allowed_tokens_fn_by_last_token
+    cfg = eval_config(args.max_his_len)
     torch.manual_seed(43)
     model = modeling.Qwen3SessionMoeWithTemperature(cfg).to(dev).eval()
-    cat = syn.make_catalogue(250_000, 1234)
+    cat = syn.make_catalogue(EVAL_TRIE_ITEMS, 1234)
     items = cat.item_sequences(2)
     fn = prefix_allowed_tokens_fn_by_last_token(flat_from_array(items), set(int(t) for t in items[:, -1]) | {syn.PAD})
-    users, beams = args.eval_users, 20
+    users, beams = args.eval_users, EVAL_BEAMS
     lo, hi = shard_range(users, rank, world)
     batch, _ = syn.make_eval_batch(cat, users, max_his_len=args.max_his_len, target_behavior=2, seed=77, full_length=True)
     host = {k: v[lo:hi].contiguous().pin_memory() for k, v in batch.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
+    n = hi - lo
+    gen_host = torch.empty(n * beams, 4, dtype=torch.int64).pin_memory()
+    score_host = torch.empty(n * beams, dtype=torch.float32).pin_memory()
 
     def decode(b):
         return model.generate(**b, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=beams,
                               num_return_sequences=beams, output_scores=True, return_dict_in_generate=True)
 
+    for _ in range(3):
+        decode(resident)
+    # one profiled call: CUDA events around every entry point (kernel breakdown + the dominant kernel's launch duration)
+    prof = _cabi.Profile()
+    _cabi.set_profile(prof)
     decode(resident)
-    iters = 3
+    torch.cuda.synchronize()
+    _cabi.set_profile(None)
+    summ = prof.summary()
+    iters = args.eval_iters
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out = {}
     for name in ("value", "e2e"):
@@ -177,21 +273,43 @@ def eval_leg(args, dev, world, rank, barrier):
                 o = decode(resident)
             else:
                 o = decode({k: v.to(dev, non_blocking=True) for k, v in host.items()})
-                seq_host, score_host = o.sequences.cpu(), o.sequences_scores.cpu()
+                # the result of an evaluation call: the decoded item tuples (the 4 new tokens of every hypothesis) and
+                # their scores; the prompts are the caller's own input and stay where they are
+                gen_host.copy_(o.generated, non_blocking=True)
+                score_host.copy_(o.sequences_scores, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         ev1.record()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[name] = users * iters / (float(t.item()) / 1e3)
-    n = hi - lo
-    return {"metric": "eval_users_per_s", "value": out["value"], "unit": "users/s",
-            "config": {"workload": f"Qwen3SessionMoe trie-constrained beam search (configs[2]), max_his_len={args.max_his_len}, "
-                                   f"prompt 501 tokens, {users} users per batch, {beams} beams, 4 new tokens, "
-                                   f"250k-item trie", "users_per_gpu": n, "iters": iters},
-            "e2e": {"value": out["e2e"], "unit": "users/s",
-                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * world,
-                    "d2h_bytes_per_step": int(seq_host.numel() * 8 + score_host.numel() * 4) * world}}
+    obj = {"metric": "eval_users_per_s", "value": out["value"], "unit": "users/s",
+           "config": {"workload": f"Qwen3SessionMoe trie-constrained beam search (configs[2]), max_his_len={args.max_his_len}, "
+                                  f"prompt 501 tokens, {users} users per batch, {beams} beams, 4 new tokens, "
+                                  f"{EVAL_TRIE_ITEMS // 1000}k-item trie", "users_per_gpu": n, "iters": iters},
+           "e2e": {"value": out["e2e"], "unit": "users/s",
+                   "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * world,
+                   "d2h_bytes_per_step": int(gen_host.numel() * 8 + score_host.numel() * 4) * world}}
+    if rank == 0 and summ:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        total = sum(v["ms"] for v in summ.values()) or 1.0
+        name, top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        if top["flops"] > 0:
+            ach, peak, unit, bound = top["flops"] / (top["ms"] / 1e3) / 1e12, peaks.get("bf16_tflops_sustained", 1400.0), "TFLOP/s", "tensor"
+        else:
+            ach, peak, unit, bound = top["bytes"] / (top["ms"] / 1e3) / 1e9, peaks.get("hbm_gbs", 6650.0), "GB/s", "hbm"
+        obj["roofline"] = {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                           "traffic": None, "share_of_call": top["ms"] / total, "avg_launch_ms": top["ms"] / max(1, top["calls"]),
+                           "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"}
+        obj["kernel_breakdown"] = {k: {"ms_per_call": v["ms"], "share": v["ms"] / total, "launches": v["calls"]}
+                                   for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:10]}
+        obj["gpu_launches_per_call"] = prof.launches
+    return obj
 
 
 def run_reference(args):
@@ -222,6 +340,13 @@ def run_reference(args):
                              "sample": f"{rows} full-length rows (L={L}) per step: fwd+bwd+clip+AdamW, fp32, oracle port of "
                                        f"the reference's PyTorch path"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_eval:
+        ev = cpu_eval_baseline(args, args.cpu_eval_users)
+        line["eval"] = {"metric": "eval_users_per_s", "value": ev["value"], "unit": "users/s", "cpu_baseline": ev,
+                        "config": {"workload": f"Qwen3SessionMoe trie-constrained beam search (configs[2]), "
+                                               f"max_his_len={args.max_his_len}, prompt 501 tokens, {EVAL_BEAMS} beams, 4 new "
+                                               f"tokens, {EVAL_TRIE_ITEMS // 1000}k-item trie; bounded sample: {ev['sample']}"},
+                        "e2e": {"value": ev["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
@@ -433,6 +558,10 @@ def main():
             line["cpu_baseline"] = {"value": rows / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"{rows} full-length rows (L={L}) per step x {n_cpu} steps after 1 warm-up: "
                                               f"fwd+bwd+clip+AdamW, fp32 oracle port"}
+            if eval_obj is not None:
+                line["eval"]["cpu_baseline"] = cpu_eval_baseline(args, args.cpu_eval_users)
+        if world == 1 and not args.no_gpu_baseline:
+            line["gpu_baseline"] = gpu_baseline_leg(args, dev)
         emit(line)
     if world > 1:
         dist.barrier()

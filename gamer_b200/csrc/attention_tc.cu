@@ -165,7 +165,7 @@ __device__ __forceinline__ void issue_nt_128x128x64(uint32_t d_tmem, uint32_t sa
     if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, k != 0);
-        umma_commit(bar0);
+        if (bar0 != nullptr) umma_commit(bar0);
         if (bar1 != nullptr) umma_commit(bar1);
     }
     __syncwarp();
@@ -539,7 +539,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if constexpr (DROP) keep_row = p.keep + ((size_t)bh * p.q_tiles + qt) * (size_t)(p.Lp >> 5) * BT + row;
         float m = -INFINITY, l = 0.f;
         int kst = 0;
-        uint32_t kph = 0;
         Trace tr = p.tr;
         if (blockIdx.x != 0 || threadIdx.x != 0) tr.buf = nullptr;
         int tn = 0;
@@ -549,12 +548,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint8_t* sc = smem + S_OFF_C + kst * S_CODES;
             const uint32_t t_s = t_row + (n & 1) * 64;
             trace_pt(tr, 1, tn, 20);
-            mbar_wait(&k_full[kst], kph);   // key codes of this stage
-            trace_pt(tr, 1, tn, 21);
-            const int mode = classify_block<KIND>(reinterpret_cast<const int4*>(sc + 512)[hf], wr, j0);
+            // S(n) was issued after K(n) and its key codes had landed: one wait covers both
             mbar_wait(&s_full[n & 1], (n >> 1) & 1);
             trace_pt(tr, 1, tn, 22);
             tc_fence_after();
+            const int mode = classify_block<KIND>(reinterpret_cast<const int4*>(sc + 512)[hf], wr, j0);
             uint32_t s[32];
             bool rescale = false;
             float m_old = m, m_new = m;
@@ -605,10 +603,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_before();
             mbar_arrive(&p_full[n & 1]);
             trace_pt(tr, 1, tn, 24);
-            if (++kst == S_KST) {
-                kst = 0;
-                kph ^= 1;
-            }
+            if (++kst == S_KST) kst = 0;
         }
         // ---- epilogue: merge the two halves, O / l (or the V column mean on uniform rows) -> bf16 -> smem (the dead Q
         // tile) -> TMA store.  Thread (row, hf) writes head-dim columns [32 hf, 32 hf + 32).
@@ -809,13 +804,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* kv_free = bars + 2;    // [2]
     uint64_t* qdo_full = bars + 4;   // [2]
     uint64_t* qdo_free = bars + 6;   // [2]
-    uint64_t* s_full = bars + 8;
-    uint64_t* s_free = bars + 9;     // all softmax threads have read S
-    uint64_t* dp_full = bars + 10;
-    uint64_t* dp_free = bars + 11;   // all softmax threads have read dP
+    uint64_t* sdp_full = bars + 8;   // S and dP of a step in TMEM (one commit behind both MMAs)
+    uint64_t* sdp_free = bars + 9;   // all softmax threads have read S and dP
     uint64_t* pds_full = bars + 12;  // P and dS tiles written
-    uint64_t* p_free = bars + 13;
-    uint64_t* ds_free = bars + 14;
+    uint64_t* pds_free = bars + 13;  // dV, dK and dQ of the step complete: the P / dS tiles may be overwritten
     uint64_t* dq_full = bars + 15;   // [2]: dQ lives in two TMEM buffers, so dQ(n) does not wait for the drain of dQ(n-1)
     uint64_t* dq_free = bars + 17;   // [2]
     uint64_t* dkv_full = bars + 19;
@@ -840,13 +832,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&dq_full[s], 1);
             mbar_init(&dq_free[s], 128);
         }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 256);
-        mbar_init(dp_full, 1);
-        mbar_init(dp_free, 256);
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_free, 256);
         mbar_init(pds_full, 256);
-        mbar_init(p_free, 1);
-        mbar_init(ds_free, 1);
+        mbar_init(pds_free, 1);
         mbar_init(dkv_full, 1);
         mbar_init(dkv_free, 128);
         fence_barrier_init();
@@ -919,14 +908,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             {   // first step of the item: S and dP (the previous item's last step has released both buffers)
                 const int st = step_n & 1;
                 mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
-                if (step_n > 0) {
-                    mbar_wait(s_free, (step_n - 1) & 1);
-                    mbar_wait(dp_free, (step_n - 1) & 1);
-                }
+                if (step_n > 0) mbar_wait(sdp_free, (step_n - 1) & 1);
                 tc_fence_after();
                 const uint32_t sq = smem_u32(smem + B_OFF_QDO + st * B_QDO_STAGE);
-                issue_nt_128x128x64(tmem_base + T_S, sq, sk, s_full);
-                issue_nt_128x128x64(tmem_base + T_DP, sq + TILE_BYTES, sv, dp_full);
+                issue_nt_128x128x64(tmem_base + T_S, sq, sk, nullptr);
+                issue_nt_128x128x64(tmem_base + T_DP, sq + TILE_BYTES, sv, sdp_full);
             }
             for (int n = 0; n < N; ++n, ++step_n) {
                 const int st = step_n & 1;
@@ -935,20 +921,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 trace_pt(tr, 0, tn, 1);
                 if (n + 1 < N) {
                     mbar_wait(&qdo_full[st ^ 1], ((step_n + 1) >> 1) & 1);
-                    mbar_wait(s_free, step_n & 1);
+                    mbar_wait(sdp_free, step_n & 1);
                     trace_pt(tr, 0, tn, 2);
                     tc_fence_after();
-                    issue_nt_128x128x64(tmem_base + T_S, sqn, sk, s_full);                   // S(n+1) = Q K^T
-                    mbar_wait(dp_free, step_n & 1);
-                    tc_fence_after();
-                    issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv, dp_full);    // dP(n+1) = dO V^T
+                    issue_nt_128x128x64(tmem_base + T_S, sqn, sk, nullptr);                  // S(n+1) = Q K^T
+                    issue_nt_128x128x64(tmem_base + T_DP, sqn + TILE_BYTES, sv, sdp_full);   // dP(n+1) = dO V^T
                 }
                 trace_pt(tr, 0, tn, 3);
                 mbar_wait(pds_full, step_n & 1);
                 trace_pt(tr, 0, tn, 4);
                 if (n == 0 && item_n > 0) mbar_wait(dkv_free, (item_n - 1) & 1);  // dK/dV of the previous item drained
                 tc_fence_after();
-                issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0, p_free);   // dV += P^T dO
+                issue_tn_128x64x128(tmem_base + T_DV, sp, sq + TILE_BYTES, n > 0, nullptr);  // dV += P^T dO
                 // Q / dO of this step are dead once dK is done: dQ reads dS and K only
                 issue_tn_128x64x128(tmem_base + T_DK, sds, sq, n > 0, &qdo_free[st]);        // dK += dS^T Q
                 const uint32_t db = step_n & 1, du = step_n >> 1;
@@ -958,7 +942,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 const bool last = n + 1 == N;
                 trace_pt(tr, 0, tn, 5);
-                issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false, &dq_full[db], ds_free,   // dQ = dS K
+                issue_nn_128x64x128(tmem_base + T_DQ + db * 64, sds, sk, false, &dq_full[db], pds_free,  // dQ = dS K
                                     last ? dkv_full : nullptr, last ? &kv_free[ks] : nullptr);
             }
         }
@@ -1049,7 +1033,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     // per-row scalars travel with the Q / dO stage (padded copies: lse' = +inf, dsum' = 0 past L)
                     const int st = step_n & 1;
                     trace_pt(tr, trole, tn, 10);
-                    mbar_wait(&qdo_full[st], (step_n >> 1) & 1);
+                    // S / dP of the step were issued after the Q / dO stage (row scalars included) had landed
+                    mbar_wait(sdp_full, step_n & 1);
+                    tc_fence_after();
                     const float* rowf = reinterpret_cast<const float*>(smem + B_OFF_QDO + st * B_QDO_STAGE + 2 * TILE_BYTES);
                     const float lse_i = rowf[row], dsum_i = rowf[128 + row];
                     const int act_i = reinterpret_cast<const int*>(rowf)[256 + row];
@@ -1062,10 +1048,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const float pu = uni ? p.inv_L : 0.f;
                     const float neg_lse = -lse_i;       // -inf on uniform / padding rows: exp2 -> 0
                     const float neg_dsum = -dsum_i;
-                    trace_pt(tr, trole, tn, 11);
-                    mbar_wait(s_full, step_n & 1);
-                    mbar_wait(dp_full, step_n & 1);
-                    tc_fence_after();
                     trace_pt(tr, trole, tn, 12);
 #pragma unroll 1
                     for (int bk = 0; bk < 2; ++bk) {
@@ -1079,8 +1061,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             for (int x = 0; x < 16; ++x) pk[x] = ds[x] = 0u;
                             if (bk == 1) {   // nothing to read from TMEM: release S and dP
                                 tc_fence_before();
-                                mbar_arrive(s_free);
-                                mbar_arrive(dp_free);
+                                mbar_arrive(sdp_free);
                             }
                         } else {
                             uint32_t s[32], dp[32];
@@ -1090,8 +1071,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             trace_pt(tr, trole, tn, 13);
                             if (bk == 1) {
                                 tc_fence_before();
-                                mbar_arrive(s_free);
-                                mbar_arrive(dp_free);
+                                mbar_arrive(sdp_free);
                             }
                             uint32_t kw = 0xffffffffu;
                             if constexpr (DROP) kw = uni ? 0xffffffffu : keep_s[bk * BT];
@@ -1107,10 +1087,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                                                      i, istart, p.scale_log2, neg_lse, neg_dsum, pu, lim_u, kw);
                         }
                         trace_pt(tr, trole, tn, 14);
-                        if (bk == 0 && step_n > 0) {
-                            mbar_wait(p_free, (step_n - 1) & 1);
-                            mbar_wait(ds_free, (step_n - 1) & 1);
-                        }
+                        if (bk == 0 && step_n > 0) mbar_wait(pds_free, (step_n - 1) & 1);
                         trace_pt(tr, trole, tn, 15);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
