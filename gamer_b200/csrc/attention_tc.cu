@@ -1206,6 +1206,306 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// =================================================================================================================
+// decode: one new token per beam row against the user's prompt K/V (constrained beam search, generation.py)
+// =================================================================================================================
+// CTA = (user, kv head).  The 2 x beams query vectors of the group (head hh of the group at tile rows [64 hh, 64 hh +
+// beams)) meet the user's prompt keys — stored once per user, shared by all beams — as tcgen05 tiles: S = Q K^T over 64
+// keys into TMEM, online softmax with one query row per thread, P (bf16) through shared memory, O += P V.  The beam's own
+// generated keys (<= 4, reached through the ancestry table) are folded in by the row's thread in the epilogue.
+constexpr int DC_KT = 64;
+constexpr int DC_THREADS = 192;                          // 4 softmax warps | MMA issuer | TMA producer
+constexpr int DC_OFF_Q = 0;                              // [128 x 64]
+constexpr int DC_OFF_K = TILE_BYTES;                     // 2 stages of [64 x 64]
+constexpr int DC_OFF_V = DC_OFF_K + 2 * S_HALF;
+constexpr int DC_OFF_P = DC_OFF_V + 2 * S_HALF;          // [128 x 64] bf16, K-major
+constexpr int DC_OFF_OK = DC_OFF_P + TILE_BYTES;         // one bit per prompt key (<= 4096 keys)
+constexpr int DC_OFF_TL = DC_OFF_OK + 512;               // list of key tiles that hold an allowed key (<= 64) + count
+constexpr int DC_OFF_BAR = DC_OFF_TL + 512;
+constexpr int DC_SMEM = DC_OFF_BAR + 128 + 1024;
+
+struct DecParams {
+    const bf16* qcur;        // [R, ld_g], q head h at column h*64
+    const bf16* gen_k;       // generated keys: step s, slot r at gen_k + s*gen_step_stride + r*ld_g (+ kvh*64)
+    const bf16* gen_v;
+    long long gen_step_stride, ld_g;
+    const int* anc;          // [R, S_max] slot of this row's ancestor at step s
+    int B, beams, L0, n_gen, n_q, n_kv, S_max;
+    const int* am;           // [B, L0]
+    const int* act;          // [B, L0] or nullptr
+    const int* sess;         // [B, L0] or nullptr
+    int kind;
+    const float* vmean;      // [B, n_kv, 64] mean of ALL L0 prompt values (cross kinds)
+    float scale_log2;
+    bf16* o;                 // [R, ld_o]
+    long long ld_o;
+};
+
+__global__ void __launch_bounds__(DC_THREADS, 3)
+attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, DecParams a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DC_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;   // [2]
+    uint64_t* v_full = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_free = bars + 6;   // all softmax threads have read S
+    uint64_t* p_full = bars + 7;   // P stored, O rescaled
+    uint64_t* pv_done = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint32_t* ok_bits = reinterpret_cast<uint32_t*>(smem + DC_OFF_OK);
+    int* tiles = reinterpret_cast<int*>(smem + DC_OFF_TL);   // [0] = count, [1..] = tile indices
+
+    const int u = blockIdx.x, kvh = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool cross = (a.kind == MASK_MULTI_CROSS || a.kind == MASK_SESSION_CROSS);
+    const int kt_all = (a.L0 + DC_KT - 1) / DC_KT;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmQ);
+        prefetch_tmap(&tmK);
+        prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<128>(tmem_slot);
+    {   // allowed-key bits of the new token's row against the prompt (Qwen3Multi/model.py:605-617, 717-728): every valid
+        // key, restricted by behaviour level / session of the last prompt token for the cross kinds
+        int act_last = 0, sess_last = 0;
+        if (cross) {
+            act_last = a.act[(long long)u * a.L0 + a.L0 - 1];
+            if (a.sess) sess_last = a.sess[(long long)u * a.L0 + a.L0 - 1];
+        }
+        for (int j0 = warp * 32; j0 < kt_all * DC_KT; j0 += DC_THREADS) {
+            const int j = j0 + lane;
+            int ok = 0;
+            if (j < a.L0) {
+                const long long idx = (long long)u * a.L0 + j;
+                ok = a.am[idx];
+                if (cross) {
+                    ok = ok && (a.act[idx] < act_last);
+                    if (a.kind == MASK_SESSION_CROSS) ok = ok && (a.sess[idx] < sess_last);
+                }
+            }
+            const unsigned w = __ballot_sync(0xffffffffu, ok != 0);
+            if (lane == 0) ok_bits[j0 >> 5] = w;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {   // key tiles with at least one allowed key
+        int n = 0;
+        for (int t = 0; t < kt_all; ++t)
+            if ((ok_bits[2 * t] | ok_bits[2 * t + 1]) != 0u) tiles[1 + n++] = t;
+        tiles[0] = n;
+    }
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkt = tiles[0];
+    const uint32_t sq = smem_u32(smem + DC_OFF_Q);
+    const uint32_t sp = smem_u32(smem + DC_OFF_P);
+    constexpr uint32_t T_O = 64;
+
+    if (warp == 5) {
+        // ===================== TMA producer =====================
+        if (lane == 0 && nkt > 0) {
+            mbar_expect_tx(q_full, 2 * a.beams * 128);
+            tma_load_2d(smem + DC_OFF_Q, &tmQ, q_full, (2 * kvh) * D, u * a.beams);
+            tma_load_2d(smem + DC_OFF_Q + 64 * 128, &tmQ, q_full, (2 * kvh + 1) * D, u * a.beams);
+            for (int n = 0; n < nkt; ++n) {
+                const int st = n & 1, t = tiles[1 + n];
+                if (n >= 2) mbar_wait(pv_done, n & 1);   // PV(n-2) done: both its K (S(n-2) came first) and V are dead
+                mbar_expect_tx(&k_full[st], S_HALF);
+                tma_load_3d(smem + DC_OFF_K + st * S_HALF, &tmK, &k_full[st], kvh * D, t * DC_KT, u);
+                mbar_expect_tx(&v_full[st], S_HALF);
+                tma_load_3d(smem + DC_OFF_V + st * S_HALF, &tmV, &v_full[st], kvh * D, t * DC_KT, u);
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        auto issue_s = [&](int n) {   // S(n)[128 x 64] = Q K_n^T
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(&k_full[n & 1], (n >> 1) & 1);
+            if (n > 0) mbar_wait(s_free, (n - 1) & 1);
+            tc_fence_after();
+            const uint64_t da = desc_k(sq), db = desc_k(smem_u32(smem + DC_OFF_K + (n & 1) * S_HALF));
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, k != 0);
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        if (nkt > 0) {
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int n = 0; n < nkt; ++n) {
+                if (n + 1 < nkt) issue_s(n + 1);
+                mbar_wait(p_full, n & 1);
+                mbar_wait(&v_full[n & 1], (n >> 1) & 1);
+                tc_fence_after();
+                constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+                const uint64_t da = desc_k(sp), db = desc_mn(smem_u32(smem + DC_OFF_V + (n & 1) * S_HALF), S_HALF);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + T_O, da + 2 * k, db + k * 128, idesc, (n > 0 || k != 0) ? 1u : 0u);
+                    umma_commit(pv_done);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== softmax warps: one query row per thread =====================
+        const int row = warp * 32 + lane;
+        const int beam = row & 63, hh = row >> 6;
+        const bool valid = beam < a.beams;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float m = -INFINITY, l = 0.f;
+        for (int n = 0; n < nkt; ++n) {
+            const int t = tiles[1 + n];
+            mbar_wait(s_full, n & 1);
+            tc_fence_after();
+            uint32_t s0[32], s1[32];
+            tmem_ld_32x32(t_row, s0);
+            tmem_ld_32x32(t_row + 32, s1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            const uint32_t w0 = ok_bits[2 * t], w1 = ok_bits[2 * t + 1];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float v0 = ((w0 >> c) & 1u) ? __uint_as_float(s0[c]) : -INFINITY;
+                const float v1 = ((w1 >> c) & 1u) ? __uint_as_float(s1[c]) : -INFINITY;
+                s0[c] = __float_as_uint(v0);
+                s1[c] = __float_as_uint(v1);
+                mx = max3(mx, v0, v1);
+            }
+            const float m_new = fmaxf(m, mx * a.scale_log2);
+            const float alpha = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new);   // (m_new finite: the tile has an allowed key)
+            const float neg_m = -m_new;
+            float sum = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float e0 = ex2_approx(fmaf(__uint_as_float(s0[c]), a.scale_log2, neg_m));
+                const float e1 = ex2_approx(fmaf(__uint_as_float(s0[c + 1]), a.scale_log2, neg_m));
+                const float f0 = ex2_approx(fmaf(__uint_as_float(s1[c]), a.scale_log2, neg_m));
+                const float f1 = ex2_approx(fmaf(__uint_as_float(s1[c + 1]), a.scale_log2, neg_m));
+                sum += (e0 + e1) + (f0 + f1);
+                pk[c >> 1] = pack_bf16(e0, e1);
+                pk[16 + (c >> 1)] = pack_bf16(f0, f1);
+            }
+            l = l * alpha + sum;
+            m = m_new;
+            if (n > 0) {   // PV(n-1) has read P and written O: rescale O, then overwrite P
+                mbar_wait(pv_done, (n - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) rescale_o_row64(t_row + T_O, alpha);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                sts128(sp + row * 128 + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        if (nkt > 0) {
+            mbar_wait(pv_done, (nkt - 1) & 1);
+            tc_fence_after();
+        }
+        // ---- epilogue: the beam's own generated keys (current token included), normalisation, store
+        float o[64];
+        {
+            uint32_t r0[32], r1[32];
+            if (nkt > 0) {
+                tmem_ld_32x32(t_row + T_O, r0);
+                tmem_ld_32x32(t_row + T_O + 32, r1);
+                tmem_ld_wait();
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                o[c] = nkt > 0 ? __uint_as_float(r0[c]) : 0.f;
+                o[32 + c] = nkt > 0 ? __uint_as_float(r1[c]) : 0.f;
+            }
+        }
+        if (valid) {
+            const int r = u * a.beams + beam, h = kvh * 2 + hh;
+            const bf16* qp = a.qcur + (long long)r * a.ld_g + h * D;
+            if (!cross) {                       // generated columns are masked for the cross rows (model.py:605-617)
+                for (int s = 0; s < a.n_gen; ++s) {
+                    const int slot = a.anc[(long long)r * a.S_max + s];
+                    const bf16* kp = a.gen_k + s * a.gen_step_stride + (long long)slot * a.ld_g + kvh * D;
+                    const bf16* vp = a.gen_v + s * a.gen_step_stride + (long long)slot * a.ld_g + kvh * D;
+                    float sc = 0.f;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float q8[8], k8[8];
+                        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(qp + c8 * 8), q8);
+                        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(kp + c8 * 8), k8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sc = fmaf(q8[e], k8[e], sc);
+                    }
+                    sc *= a.scale_log2;
+                    const float m_new = fmaxf(m, sc);
+                    const float alpha = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new), pe = ex2_approx(sc - m_new);
+                    l = l * alpha + pe;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float v8[8];
+                        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(vp + c8 * 8), v8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[c8 * 8 + e] = o[c8 * 8 + e] * alpha + pe * v8[e];
+                    }
+                    m = m_new;
+                }
+            }
+            if (l > 0.f) {
+                const float inv = 1.f / l;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) o[c] *= inv;
+            } else {
+                // no allowed key: uniform over ALL cached keys (quirk Q1) = (L0 * mean(prompt V) + sum gen V) / (L0 + n_gen)
+                const float* vm = a.vmean + ((long long)u * a.n_kv + kvh) * D;
+                const float inv = 1.0f / (float)(a.L0 + a.n_gen);
+#pragma unroll
+                for (int c = 0; c < 64; ++c) o[c] = vm[c] * (float)a.L0;
+                for (int s = 0; s < a.n_gen; ++s) {
+                    const int slot = a.anc[(long long)r * a.S_max + s];
+                    const bf16* vp = a.gen_v + s * a.gen_step_stride + (long long)slot * a.ld_g + kvh * D;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float v8[8];
+                        bf16x8_to_float(*reinterpret_cast<const bf16x8*>(vp + c8 * 8), v8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[c8 * 8 + e] += v8[e];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 64; ++c) o[c] *= inv;
+            }
+            bf16* op = a.o + (long long)r * a.ld_o + h * D;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<bf16x8*>(op + c8 * 8) = float_to_bf16x8(o + c8 * 8);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<128>(tmem_base);
+}
+
 // Padded per-row inputs of the backward: dsum_p[b,h,i] = keep_prob * sum_d dO*O and lse_p[b,h,i] = lse + log2(keep_prob)
 // (so that exp2(s - lse_p) = P / keep_prob); uniform rows keep dsum unscaled and lse = +inf; rows i >= L: 0 / +inf.
 // uni_bits[b] |= 1 << (i / 128) for uniform rows (head 0 decides: the mask is head-independent).
@@ -1484,5 +1784,41 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
         default: e = launch_bwd<3>(tq, tk, tv, tdo, tdk, tdv, p, stream); break;
     }
     if (e) return e;
+    return 0;
+}
+
+int attn_tc_decode(const void* qcur, const void* pk, const void* pv, long long ld_p, const void* gen_k, const void* gen_v,
+                   long long gen_step_stride, long long ld_g, const int* anc, int B, int beams, int L0, int n_gen, int n_q,
+                   int n_kv, int S_max, const int* am, const int* act, const int* sess, int kind, const float* vmean,
+                   float scale, void* o, long long ld_o, cudaStream_t stream) {
+    CUtensorMap tq, tk, tv;
+    {   // q rows of this step: [R, ld_g] viewed as one "sequence"; box = [64 columns x beams rows]
+        EncodeTiledFn fn = encode_fn();
+        GAMER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        GAMER_REQUIRE((reinterpret_cast<uintptr_t>(qcur) & 15) == 0 && (ld_g * 2) % 16 == 0, "decode q rows must be 16-byte aligned");
+        cuuint64_t dims[2] = {(cuuint64_t)n_q * D, (cuuint64_t)B * beams};
+        cuuint64_t strides[1] = {(cuuint64_t)ld_g * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)beams};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qcur), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        GAMER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (decode q) failed with %d", (int)r);
+    }
+    if (int e = make_tmap_seq(&tk, pk, B, L0, n_kv * D, ld_p, DC_KT)) return e;
+    if (int e = make_tmap_seq(&tv, pv, B, L0, n_kv * D, ld_p, DC_KT)) return e;
+    DecParams a{};
+    a.qcur = reinterpret_cast<const bf16*>(qcur);
+    a.gen_k = reinterpret_cast<const bf16*>(gen_k); a.gen_v = reinterpret_cast<const bf16*>(gen_v);
+    a.gen_step_stride = gen_step_stride; a.ld_g = ld_g; a.anc = anc;
+    a.B = B; a.beams = beams; a.L0 = L0; a.n_gen = n_gen; a.n_q = n_q; a.n_kv = n_kv; a.S_max = S_max;
+    a.am = am; a.act = act; a.sess = sess; a.kind = kind; a.vmean = vmean;
+    a.scale_log2 = scale * 1.4426950408889634f;
+    a.o = reinterpret_cast<bf16*>(o); a.ld_o = ld_o;
+    static PerDeviceOnce cfg;
+    if (cfg.need())
+        GAMER_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM));
+    attn_decode_kernel<<<dim3(B, n_kv), DC_THREADS, DC_SMEM, stream>>>(tq, tk, tv, a);
+    GAMER_LAUNCH_CHECK();
     return 0;
 }

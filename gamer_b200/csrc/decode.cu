@@ -1,178 +1,18 @@
 // K9: constrained beam-search decode.
 //   * attn_decode   — one new token per beam row against the user's prompt K/V (stored once per user, shared by all
-//                     beams) plus the beam's own generated K/V reached through an ancestry table (no cache reorder);
+//                     beams) plus the beam's own generated K/V reached through an ancestry table (no cache reorder): the
+//                     tcgen05 kernel attn_decode_kernel of attention_tc.cu;
 //   * trie_init     — walk the flat (CSR) candidate trie from the suffix after the last item-terminating token
 //                     (SeqRec/generation/trie.py:92-104);
 //   * beam_step     — fused full-vocab log-softmax + trie-child mask + running-score add + per-user top-K in shared
 //                     memory with warp shuffles (HF _beam_search + PrefixConstrainedLogitsProcessor as driven by
 //                     SeqRec/tasks/test_SMB_decoder.py:159-177; the mask is applied AFTER normalisation, quirk Q6).
+#include "attention_tc.cuh"
 #include "common.cuh"
 
 namespace {
 
 constexpr int D = 64;
-constexpr int KROW = 66;   // padded smem row (bf16) -> conflict-free column access
-
-struct DecodeArgs {
-    const bf16* qcur;        // [R, ld_g], q head h at column h*64
-    const bf16* pk;          // prompt keys   [B*L0, ld_p] (+ kvh*64)
-    const bf16* pv;          // prompt values
-    long long ld_p;
-    const bf16* gen_k;       // generated keys: step s, slot r at gen_k + s*gen_step_stride + r*ld_g (+ kvh*64)
-    const bf16* gen_v;
-    long long gen_step_stride, ld_g;
-    const int* anc;          // [R, S_max] slot of this row's ancestor at step s
-    int B, beams, L0, n_gen, n_q, n_kv, S_max;
-    const int* am;           // [B, L0]
-    const int* act;          // [B, L0] or nullptr
-    const int* sess;         // [B, L0] or nullptr
-    int kind;
-    const float* vmean;      // [B, n_kv, 64] mean of ALL L0 prompt values (cross kinds)
-    float scale_log2;
-    bf16* o;                 // [R, ld_o]
-    long long ld_o;
-};
-
-__global__ void __launch_bounds__(256) attn_decode_kernel(DecodeArgs a) {
-    __shared__ bf16 sK[64 * KROW];
-    __shared__ bf16 sV[64 * KROW];
-    __shared__ int sOk[64];
-    extern __shared__ float sQ[];   // [n_queries][64] fp32
-
-    const int u = blockIdx.x, kvh = blockIdx.y;
-    const int group = a.n_q / a.n_kv;
-    const int nqv = a.beams * group;          // query vectors handled by this CTA
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool cross = (a.kind == MASK_MULTI_CROSS || a.kind == MASK_SESSION_CROSS);
-
-    for (int x = threadIdx.x; x < nqv * D; x += blockDim.x) {
-        const int qi = x / D, d = x % D;
-        const int r = u * a.beams + qi / group, h = kvh * group + qi % group;
-        sQ[x] = __bfloat162float(a.qcur[(long long)r * a.ld_g + h * D + d]);
-    }
-    int act_last = 0, sess_last = 0;
-    if (cross) {
-        act_last = a.act[(long long)u * a.L0 + a.L0 - 1];
-        if (a.sess) sess_last = a.sess[(long long)u * a.L0 + a.L0 - 1];
-    }
-    constexpr int QPW = 8;                       // queries per warp (8 warps x 8 >= 40 for 20 beams x 2 heads)
-    float m[QPW], l[QPW], acc0[QPW], acc1[QPW];
-#pragma unroll
-    for (int i = 0; i < QPW; ++i) {
-        m[i] = -INFINITY;
-        l[i] = 0.f;
-        acc0[i] = acc1[i] = 0.f;
-    }
-    const int n_tiles = (a.L0 + 63) / 64;
-    for (int t = 0; t < n_tiles; ++t) {
-        __syncthreads();
-        const int j0 = t * 64;
-        for (int x = threadIdx.x; x < 64 * 8; x += blockDim.x) {
-            const int row = x >> 3, ch = x & 7;
-            const int j = j0 + row;
-            uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-            if (j < a.L0) {
-                kk = *reinterpret_cast<const uint4*>(a.pk + ((long long)u * a.L0 + j) * a.ld_p + kvh * D + ch * 8);
-                vv = *reinterpret_cast<const uint4*>(a.pv + ((long long)u * a.L0 + j) * a.ld_p + kvh * D + ch * 8);
-            }
-            uint32_t* dk = reinterpret_cast<uint32_t*>(sK + row * KROW + ch * 8);
-            uint32_t* dv = reinterpret_cast<uint32_t*>(sV + row * KROW + ch * 8);
-            dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
-            dv[0] = vv.x; dv[1] = vv.y; dv[2] = vv.z; dv[3] = vv.w;
-        }
-        if (threadIdx.x < 64) {
-            const int j = j0 + threadIdx.x;
-            int ok = 0;
-            if (j < a.L0) {
-                const long long idx = (long long)u * a.L0 + j;
-                ok = a.am[idx];
-                if (cross) {
-                    ok = ok && (a.act[idx] < act_last);
-                    if (a.kind == MASK_SESSION_CROSS) ok = ok && (a.sess[idx] < sess_last);
-                }
-            }
-            sOk[threadIdx.x] = ok;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int qq = 0; qq < QPW; ++qq) {
-            const int qi = warp + qq * 8;
-            if (qi >= nqv) break;
-            const float* qv = sQ + qi * D;
-            float s0 = 0.f, s1 = 0.f;
-            const uint32_t* k0 = reinterpret_cast<const uint32_t*>(sK + lane * KROW);
-            const uint32_t* k1 = reinterpret_cast<const uint32_t*>(sK + (lane + 32) * KROW);
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) {
-                const float2 a0 = unpack_bf16(k0[w]), a1 = unpack_bf16(k1[w]);
-                s0 += qv[2 * w] * a0.x + qv[2 * w + 1] * a0.y;
-                s1 += qv[2 * w] * a1.x + qv[2 * w + 1] * a1.y;
-            }
-            s0 = sOk[lane] ? s0 * a.scale_log2 : -INFINITY;
-            s1 = sOk[lane + 32] ? s1 * a.scale_log2 : -INFINITY;
-            const float mx = warp_max(fmaxf(s0, s1));
-            const float mnew = fmaxf(m[qq], mx);
-            if (mnew == -INFINITY) continue;           // warp-uniform
-            const float alpha = exp2f(m[qq] - mnew);
-            const float p0 = exp2f(s0 - mnew), p1 = exp2f(s1 - mnew);
-            l[qq] = l[qq] * alpha + warp_sum(p0 + p1);
-            float o0 = acc0[qq] * alpha, o1 = acc1[qq] * alpha;
-            for (int j = 0; j < 32; ++j) {
-                const float pj = __shfl_sync(0xffffffffu, p0, j);
-                const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sV + j * KROW + 2 * lane));
-                o0 += pj * v.x;
-                o1 += pj * v.y;
-            }
-            for (int j = 0; j < 32; ++j) {
-                const float pj = __shfl_sync(0xffffffffu, p1, j);
-                const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sV + (j + 32) * KROW + 2 * lane));
-                o0 += pj * v.x;
-                o1 += pj * v.y;
-            }
-            m[qq] = mnew;
-            acc0[qq] = o0;
-            acc1[qq] = o1;
-        }
-    }
-    // generated keys (the beam's own ancestry, current token included) and the epilogue
-#pragma unroll
-    for (int qq = 0; qq < QPW; ++qq) {
-        const int qi = warp + qq * 8;
-        if (qi >= nqv) break;
-        const int r = u * a.beams + qi / group, h = kvh * group + qi % group;
-        const float* qv = sQ + qi * D;
-        float gsum0 = 0.f, gsum1 = 0.f;     // unmasked sum of generated values (uniform-row fallback)
-        for (int s = 0; s < a.n_gen; ++s) {
-            const int slot = a.anc[(long long)r * a.S_max + s];
-            const bf16* kp = a.gen_k + s * a.gen_step_stride + (long long)slot * a.ld_g + kvh * D;
-            const bf16* vp = a.gen_v + s * a.gen_step_stride + (long long)slot * a.ld_g + kvh * D;
-            const float2 kv2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(kp + 2 * lane));
-            const float2 vv2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(vp + 2 * lane));
-            gsum0 += vv2.x;
-            gsum1 += vv2.y;
-            if (cross) continue;            // generated columns are masked for the cross rows (model.py:605-617)
-            float sc = warp_sum(qv[2 * lane] * kv2.x + qv[2 * lane + 1] * kv2.y) * a.scale_log2;
-            const float mnew = fmaxf(m[qq], sc);
-            const float alpha = exp2f(m[qq] - mnew), p = exp2f(sc - mnew);
-            l[qq] = l[qq] * alpha + p;
-            acc0[qq] = acc0[qq] * alpha + p * vv2.x;
-            acc1[qq] = acc1[qq] * alpha + p * vv2.y;
-            m[qq] = mnew;
-        }
-        float o0, o1;
-        if (l[qq] > 0.f) {
-            o0 = acc0[qq] / l[qq];
-            o1 = acc1[qq] / l[qq];
-        } else {
-            // no allowed key: uniform over ALL cached keys (quirk Q1) = (L0 * mean(prompt V) + sum gen V) / (L0 + n_gen)
-            const float* vm = a.vmean + ((long long)u * a.n_kv + kvh) * D;
-            const float inv = 1.0f / (float)(a.L0 + a.n_gen);
-            o0 = (vm[2 * lane] * a.L0 + gsum0) * inv;
-            o1 = (vm[2 * lane + 1] * a.L0 + gsum1) * inv;
-        }
-        *reinterpret_cast<uint32_t*>(a.o + (long long)r * a.ld_o + h * D + 2 * lane) = pack_bf16(o0, o1);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // flat trie: node n has children [child_start[n], child_start[n+1]) with tokens child_tok[] (ascending) and node
@@ -328,26 +168,17 @@ extern "C" int gamer_attn_decode(const void* qcur, const void* pk, const void* p
                                  const int* am, const int* act, const int* sess, int mask_kind, const float* vmean,
                                  float scale, void* o, long long ld_o, cudaStream_t stream) {
     GAMER_REQUIRE(head_dim == D, "decode attention is specialised for head_dim 64");
-    GAMER_REQUIRE(n_kv > 0 && n_q % n_kv == 0, "n_q must be a multiple of n_kv");
-    const int nqv = beams * (n_q / n_kv);
-    GAMER_REQUIRE(nqv <= 64, "beams * (n_q / n_kv) = %d exceeds the 64 query vectors one CTA handles", nqv);
+    GAMER_REQUIRE(n_kv > 0 && n_q == 2 * n_kv, "decode attention is specialised for two query heads per kv head (got %d / %d)",
+                  n_q, n_kv);
+    GAMER_REQUIRE(beams >= 1 && beams <= 64, "num_beams = %d exceeds the 64 beam rows one CTA handles", beams);
+    GAMER_REQUIRE(L0 >= 1 && L0 <= 4096, "prompt length %d out of range (1..4096)", L0);
     const bool cross = mask_kind == MASK_MULTI_CROSS || mask_kind == MASK_SESSION_CROSS;
     GAMER_REQUIRE(!cross || (act != nullptr && vmean != nullptr), "cross decode attention needs actions and vmean");
     GAMER_REQUIRE(mask_kind != MASK_SESSION_CROSS || sess != nullptr, "SESSION_CROSS needs session ids");
+    GAMER_REQUIRE(vmean != nullptr || !cross, "decode attention needs the prompt value mean for rows without an allowed key");
     if (B == 0) return 0;
-    DecodeArgs a;
-    a.qcur = reinterpret_cast<const bf16*>(qcur); a.pk = reinterpret_cast<const bf16*>(pk);
-    a.pv = reinterpret_cast<const bf16*>(pv); a.ld_p = ld_p;
-    a.gen_k = reinterpret_cast<const bf16*>(gen_k); a.gen_v = reinterpret_cast<const bf16*>(gen_v);
-    a.gen_step_stride = gen_step_stride; a.ld_g = ld_g; a.anc = anc;
-    a.B = B; a.beams = beams; a.L0 = L0; a.n_gen = n_gen; a.n_q = n_q; a.n_kv = n_kv; a.S_max = S_max;
-    a.am = am; a.act = act; a.sess = sess; a.kind = mask_kind; a.vmean = vmean;
-    a.scale_log2 = scale * 1.4426950408889634f;
-    a.o = reinterpret_cast<bf16*>(o); a.ld_o = ld_o;
-    dim3 grid(B, n_kv);
-    attn_decode_kernel<<<grid, 256, nqv * D * sizeof(float), stream>>>(a);
-    GAMER_LAUNCH_CHECK();
-    return 0;
+    return attn_tc_decode(qcur, pk, pv, ld_p, gen_k, gen_v, gen_step_stride, ld_g, anc, B, beams, L0, n_gen, n_q, n_kv,
+                          S_max, am, act, sess, mask_kind, vmean, scale, o, ld_o, stream);
 }
 
 extern "C" int gamer_trie_init(const long long* ids, int B, int L, int vocab, const unsigned char* last_set,

@@ -263,7 +263,9 @@ def attn_decode(qcur, prompt_rot, gen, step_stride, anc, B, beams, L0, n_gen, n_
     koff, voff = n_q * hd * esz, (n_q + n_kv) * hd * esz
     call("gamer_attn_decode", ptr(qcur), prompt_rot.data_ptr() + koff, prompt_rot.data_ptr() + voff, prompt_rot.stride(0),
          gen.data_ptr() + koff, gen.data_ptr() + voff, step_stride, qcur.stride(0), ptr(anc), B, beams, L0, n_gen, n_q,
-         n_kv, hd, S_max, ptr(am), ptr(act), ptr(sess), kind, ptr(vmean), float(scale), ptr(o), o.stride(0), _stream())
+         n_kv, hd, S_max, ptr(am), ptr(act), ptr(sess), kind, ptr(vmean), float(scale), ptr(o), o.stride(0), _stream(),
+         work=(4 * hd * n_q * R * (L0 + n_gen),                                  # QK^T + PV over every cached key
+               B * L0 * 2 * n_kv * hd * esz + R * (n_q + 2 * n_kv * n_gen + n_q) * hd * esz))   # prompt K/V once per user
     return o
 
 

@@ -226,7 +226,7 @@ def routed_ffn(spec, W, pre, h, position_index, behavior_index, inject, sparse, 
     for e in range(spec.n_experts):
         sel = position_index == e
         if sel.any():
-            out[sel] = expert(f"{pre}experts.expert_{e}.", x[sel], None if zi is None else zi[sel])
+            out[sel] = expert(f"{pre}experts.expert_{e}.", x[sel], None if zi is None else zi[sel]).to(out.dtype)
     return out
 
 
