@@ -52,17 +52,21 @@ def _resolve_constraint(prefix_allowed_tokens_fn, candidate_trie, vocab, pad, de
     else:
         raise ValueError("constrained beam search needs prefix_allowed_tokens_fn or candidate_trie")
     flat = trie if isinstance(trie, FlatTrie) else trie.flat()
-    cache = getattr(flat, "_dev_cache", None)
-    if cache is None or cache[0] != device:
-        flat._dev_cache = (device, flat.to(device))
-    flat_dev = flat._dev_cache[1]
-    bitmap = torch.zeros(vocab, dtype=torch.uint8)
-    if last is None:
-        bitmap[:] = 0          # prefix_allowed_tokens_fn: the whole sentence is the prefix
-    else:
-        idx = torch.tensor(sorted(t for t in last if 0 <= t < vocab), dtype=torch.long)
-        bitmap[idx] = 1
-    return flat_dev, bitmap.to(device)
+    # device copies are cached on the host objects: a captured decode graph holds their addresses
+    cache = flat.__dict__.setdefault("_dev_cache", {})
+    if device not in cache:
+        cache[device] = flat.to(device)
+    flat_dev = cache[device]
+    owner = prefix_allowed_tokens_fn if isinstance(prefix_allowed_tokens_fn, _PrefixFn) else flat
+    bcache = owner.__dict__.setdefault("_bitmap_cache", {})
+    bkey = (device, vocab)
+    if bkey not in bcache:
+        bitmap = torch.zeros(vocab, dtype=torch.uint8)       # last is None: the whole sentence is the prefix
+        if last is not None:
+            idx = torch.tensor(sorted(t for t in last if 0 <= t < vocab), dtype=torch.long)
+            bitmap[idx] = 1
+        bcache[bkey] = bitmap.to(device)
+    return flat_dev, bcache[bkey]
 
 
 def _decode_layer_attention(arch, d, meta, x, s, R, B, beams, L0, S_max, tabs, gen, anc, prompt, kind, norm_w, w_qkv, qn,
@@ -116,15 +120,23 @@ def decode_step(arch, pack, lut, meta, state, tokens, s):
     return E.lm_head_logits(arch, pack, hidden)
 
 
-def beam_search_core(B, beams, S, vocab, flat, node0, logits0, advance, device):
-    """The beam bookkeeping, independent of where the logits come from.
+def _raise_on(code: int):
+    if code == 1:
+        raise ValueError("`prefix_allowed_tokens_fn` returned an empty list for a beam: the prompt suffix is not a "
+                         "prefix of any candidate (cf. PrefixConstrainedLogitsProcessor)")
+    if code == 2:
+        raise RuntimeError("beam step candidate buffer overflow")
+
+
+def beam_search_device(B, beams, S, vocab, flat, node0, logits0, advance, device):
+    """The beam bookkeeping, independent of where the logits come from; no host synchronisation (graph-capturable).
 
     node0 [B] int32: trie node of every user's prompt suffix; logits0 [B*beams, >=vocab] fp32: next-token logits of the
     (identical) beams of each user; advance(s, parent_rows [R] int64, tokens [R] int64) -> logits [R, >=vocab] for the
     rows obtained by appending `tokens` to the hypotheses `parent_rows`.
-    Returns (generated tokens [B, beams, S] int64, summed log-probabilities [B, beams] fp32), best-first per user.
+    Returns (generated tokens [B, beams, S] int64, summed log-probabilities [B, beams] fp32, error word [1] int32),
+    best-first per user.
     """
-    R = B * beams
     node = node0.repeat_interleave(beams).contiguous()
     run = torch.zeros(B, beams, dtype=torch.float32, device=device)
     run[:, 1:] = -1e9                                                        # HF: beam_scores[:, 1:] = -1e9
@@ -141,39 +153,28 @@ def beam_search_core(B, beams, S, vocab, flat, node0, logits0, advance, device):
         prow = (parent.long() + row_base).view(-1)                           # parent row of every new beam row
         logits = advance(s, prow, tok.view(-1).long())
         node = node.view(-1).contiguous()
-    code = int(err.item())                                                   # single host sync of the whole decode
-    if code == 1:
-        raise ValueError("`prefix_allowed_tokens_fn` returned an empty list for a beam: the prompt suffix is not a "
-                         "prefix of any candidate (cf. PrefixConstrainedLogitsProcessor)")
-    if code == 2:
-        raise RuntimeError("beam step candidate buffer overflow")
     # backtrack the token choices through the parent pointers
     gen = torch.empty(B, beams, S, dtype=torch.long, device=device)
     idx = torch.arange(beams, device=device).view(1, beams).expand(B, beams)
     for s in reversed(range(S)):
         gen[:, :, s] = torch.gather(toks[s].long(), 1, idx)
         idx = torch.gather(parents[s].long(), 1, idx)
+    return gen, run, err
+
+
+def beam_search_core(B, beams, S, vocab, flat, node0, logits0, advance, device):
+    """beam_search_device + the error check (one host sync).  Returns (generated tokens, summed log-probabilities)."""
+    gen, run, err = beam_search_device(B, beams, S, vocab, flat, node0, logits0, advance, device)
+    _raise_on(int(err.item()))
     return gen, run
 
 
-@torch.no_grad()
-def constrained_beam_search(model, input_ids, attention_mask, session_ids, extended_session_ids, actions,
-                            max_new_tokens, prefix_allowed_tokens_fn, candidate_trie, num_beams, num_return_sequences,
-                            return_dict_in_generate=True):
-    if not input_ids.is_cuda:
-        raise RuntimeError("gamer_b200 has no CPU path: move the model and inputs to a CUDA device")
-    arch = model.arch
-    pack, lut = model._get_pack(arch)
+def _decode_on_device(arch, pack, lut, flat, last_bitmap, beams, S, input_ids, attention_mask, session_ids,
+                      extended_session_ids, actions):
+    """Prefill + constrained beam search, everything enqueued on the current stream without a host sync."""
     dev = input_ids.device
-    input_ids = input_ids.contiguous()
     B, L0 = input_ids.shape
-    beams, S = int(num_beams), int(max_new_tokens)
-    if num_return_sequences > beams:
-        raise ValueError("`num_return_sequences` has to be smaller or equal to `num_beams`.")
-    if S > arch.P - 1:
-        raise NotImplementedError(f"max_new_tokens={S}: decode emits one item (<= {arch.P - 1} code tokens) per call")
     R = B * beams
-    flat, last_bitmap = _resolve_constraint(prefix_allowed_tokens_fn, candidate_trie, arch.vocab, arch.pad, dev)
     meta = E.make_meta(arch, input_ids, attention_mask, actions, session_ids, extended_session_ids)
 
     # ---- prefill once per user; the rotated q|k|v buffers are the prompt K/V cache ------------------------------
@@ -203,7 +204,81 @@ def constrained_beam_search(model, input_ids, attention_mask, session_ids, exten
         return decode_step(arch, pack, lut, meta, state, tokens, s)
 
     node0 = K.trie_init(input_ids, arch.vocab, last_bitmap, flat)
-    gen, run = beam_search_core(B, beams, S, arch.vocab, flat, node0, logits0, advance, dev)
+    return beam_search_device(B, beams, S, arch.vocab, flat, node0, logits0, advance, dev)
+
+
+class _DecodeGraph:
+    """One captured evaluation call (prefill + 4 beam steps, ~330 kernel launches) for a fixed batch shape: replaying it
+    costs one launch on the host, which is what keeps small per-GPU shards (32 users per GPU at 8 GPUs) on the device's
+    clock instead of the host's."""
+
+    def __init__(self, fn, inputs):
+        self.static = {k: (None if v is None else v.clone()) for k, v in inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                        # warm-up outside the capture
+            fn(**self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(**self.static)
+
+    def run(self, inputs):
+        for k, v in inputs.items():
+            if v is not None:
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+MAX_DECODE_GRAPHS = 3
+
+
+@torch.no_grad()
+def constrained_beam_search(model, input_ids, attention_mask, session_ids, extended_session_ids, actions,
+                            max_new_tokens, prefix_allowed_tokens_fn, candidate_trie, num_beams, num_return_sequences,
+                            return_dict_in_generate=True):
+    if not input_ids.is_cuda:
+        raise RuntimeError("gamer_b200 has no CPU path: move the model and inputs to a CUDA device")
+    arch = model.arch
+    pack, lut = model._get_pack(arch)
+    dev = input_ids.device
+    input_ids = input_ids.contiguous()
+    B, L0 = input_ids.shape
+    beams, S = int(num_beams), int(max_new_tokens)
+    if num_return_sequences > beams:
+        raise ValueError("`num_return_sequences` has to be smaller or equal to `num_beams`.")
+    if S > arch.P - 1:
+        raise NotImplementedError(f"max_new_tokens={S}: decode emits one item (<= {arch.P - 1} code tokens) per call")
+    flat, last_bitmap = _resolve_constraint(prefix_allowed_tokens_fn, candidate_trie, arch.vocab, arch.pad, dev)
+    inputs = dict(input_ids=input_ids, attention_mask=attention_mask, session_ids=session_ids,
+                  extended_session_ids=extended_session_ids, actions=actions)
+    fn = lambda **kw: _decode_on_device(arch, pack, lut, flat, last_bitmap, beams, S, **kw)
+
+    # A batch shape seen for the second time is captured into a CUDA graph and replayed from then on (the pack, the
+    # trie and the bitmap keep their addresses; a weight update builds a new pack, hence a new key).
+    use_graphs = getattr(model.config, "gamer_decode_graphs", True) and not torch.cuda.is_current_stream_capturing()
+    key = (id(pack), id(flat), id(last_bitmap), beams, S,
+           tuple((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in inputs.items()))
+    cache = model.__dict__.setdefault("_decode_graphs", {})
+    entry = cache.get(key) if use_graphs else None
+    if isinstance(entry, _DecodeGraph):
+        gen, run, err = entry.run(inputs)
+        gen = gen.clone()                                                    # the graph's outputs are reused by the next replay
+    else:
+        if use_graphs and entry == "seen":
+            for k in [k for k in cache if k[0] != id(pack)]:                 # graphs of a retired pack
+                del cache[k]
+            while sum(isinstance(v, _DecodeGraph) for v in cache.values()) >= MAX_DECODE_GRAPHS:
+                del cache[next(k for k, v in cache.items() if isinstance(v, _DecodeGraph))]
+            cache[key] = _DecodeGraph(fn, inputs)
+            gen, run, err = cache[key].run(inputs)
+            gen = gen.clone()
+        else:
+            if use_graphs:
+                cache[key] = "seen"
+            gen, run, err = fn(**inputs)
+    _raise_on(int(err.item()))                                               # single host sync of the whole decode
     seqs = torch.cat([input_ids.view(B, 1, L0).expand(B, beams, L0), gen], dim=2)
     scores = run / float(S)                                                  # length_penalty = 1: sum / generated length
     nret = num_return_sequences

@@ -199,3 +199,94 @@ def test_generate_rejects_dead_prefix():
     fn = prefix_allowed_tokens_fn_by_last_token(Trie([[999, 20, 300, 600, 900]]), {900, 4})   # behaviour token absent
     with pytest.raises(ValueError):
         m.generate(**b, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=4)
+
+
+def _headline_eval_setup(users, seed_weights=5):
+    """configs[2] at full size: Qwen3SessionMoe (8 layers, hidden 256), max_his_len 100 (501-token prompts), 250k-item
+    candidate trie, deterministic well-separated weights."""
+    import bench
+    from gamer_b200 import modeling
+    from gamer_b200.trie import flat_from_array, prefix_allowed_tokens_fn_by_last_token
+    from oracle import oracle_model as om
+    cfg = bench.eval_config(100)
+    m = modeling.Qwen3SessionMoeWithTemperature(cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "lm_head.weight"}
+    sd = syn.seeded_state_dict(shapes, seed=seed_weights)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k == "lm_head.weight" for k in missing)
+    m.tie_weights()
+    m.set_hyper(1.0)
+    m = m.to(DEV).eval()
+    W = dict(sd)
+    W["lm_head.weight"] = W["model.embed_tokens.weight"]
+    spec = om.Spec.from_hf_config(cfg, "Qwen3SessionMoe", temperature=1.0)
+    cat = syn.make_catalogue(bench.EVAL_TRIE_ITEMS, 1234)
+    items = cat.item_sequences(2)
+    last = set(int(t) for t in items[:, -1]) | {syn.PAD}
+    fn = prefix_allowed_tokens_fn_by_last_token(flat_from_array(items), last)
+    batch, _ = syn.make_eval_batch(cat, users, max_his_len=100, target_behavior=2, seed=77, full_length=True)
+    return m, spec, W, items, last, fn, batch
+
+
+def test_generate_headline_shape_vs_oracle_and_graph_replay():
+    """BASELINE configs[2] shape (501-token prompts, 20 beams, 250k-item trie, full 8-layer Qwen3SessionMoe) on 4 users
+    against the fp32 oracle: tuples / scores under the margin rules of _check_generate, and hit / recall / ndcg@K of
+    targets planted at clearly separated ranks of the oracle's beam must be IDENTICAL.  The same call is then repeated:
+    the second call captures a CUDA graph, the third replays it — both must return the first (eager) call's bits."""
+    from gamer_b200 import ranking
+    users, K = 4, 20
+    m, spec, W, items, last, fn, batch = _headline_eval_setup(users)
+    B, L0 = batch["input_ids"].shape
+    assert L0 == 501
+    trace = []
+    with torch.no_grad():
+        ref_seqs, ref_scores = od.constrained_beam_search(
+            spec, W, od.PrefixTree(items.tolist()), last, batch["input_ids"], batch["attention_mask"],
+            batch["session_ids"], batch["extended_session_ids"], batch["actions"], num_beams=K, trace=trace)
+    b = {k: v.to(DEV) for k, v in batch.items()}
+    call = lambda: m.generate(**b, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    out = call()
+    worst, overlap = _check_generate(spec, W, batch, items, K, out, ref_seqs, ref_scores, trace=trace)
+    print(f"headline eval shape: worst |score - oracle rescoring| {worst:.3e}; overlap {overlap:.2f}")
+
+    # ranking metrics on targets planted at oracle ranks whose neighbours are further than TIE_GAP away (order is only
+    # defined away from ties) and that survived in our beam
+    ref = ref_seqs.view(B, K, -1)[:, :, L0:]
+    rs = ref_scores.view(B, K)
+    ours = out.generated.cpu().view(B, K, 4)
+    targets, checked = [], 0
+    for u in range(B):
+        mine = [tuple(t) for t in ours[u].tolist()]
+        tg = []
+        for r in range(K):
+            left = float(rs[u, r - 1] - rs[u, r]) if r > 0 else 1.0
+            right = float(rs[u, r] - rs[u, r + 1]) if r + 1 < K else 1.0
+            t = tuple(ref[u, r].tolist())
+            if left > TIE_GAP and right > TIE_GAP and t in mine and len(tg) < 3:
+                tg.append(t)
+        # (no clearly separated rank for this user: a target outside both beams keeps the user in the sums with zero hits)
+        targets.append(tg if tg else [(0, 0, 0, 0)])
+        checked += len(tg)
+    assert checked >= 2, "no clearly separated rank found to plant targets on"
+    names = ["hit@1", "hit@5", "hit@10", "recall@5", "recall@10", "ndcg@5", "ndcg@10", "ndcg@20"]
+    tstr = [["_".join(map(str, t)) for t in tg] for tg in targets]
+    to_str = lambda g: ["_".join(map(str, t)) for t in g.reshape(B * K, 4).tolist()]
+    res_ref = ranking.get_metrics_results(ranking.get_topk_results(to_str(ref), ref_scores.tolist(), tstr, K), names, tstr)
+    res_our = ranking.get_metrics_results(ranking.get_topk_results(to_str(ours), out.sequences_scores.cpu().tolist(), tstr, K),
+                                          names, tstr)
+    # a planted target keeps its rank only if no near-tied neighbour overtook it: its own margins are > TIE_GAP, so the
+    # metrics must agree exactly
+    for n in names:
+        assert abs(res_ref[n] - res_our[n]) <= 1e-9, (n, res_ref[n], res_our[n])
+
+    out2 = call()       # captures the graph for this shape
+    out3 = call()       # replays it
+    assert "_decode_graphs" in m.__dict__ and any(not isinstance(v, str) for v in m._decode_graphs.values())
+    for o in (out2, out3):
+        assert torch.equal(o.sequences, out.sequences) and torch.equal(o.generated, out.generated)
+        assert torch.equal(o.sequences_scores, out.sequences_scores)
+    # a replay with different inputs of the same shape must follow the inputs (static buffers are refreshed)
+    perm = torch.tensor([1, 0, 3, 2], device=DEV)
+    b2 = {k: v[perm].contiguous() for k, v in b.items()}
+    out4 = m.generate(**b2, max_new_tokens=4, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    assert torch.equal(out4.generated.view(B, K, 4), out.generated.view(B, K, 4)[perm])
