@@ -18,6 +18,7 @@ from __future__ import annotations
 import os
 import sys
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -99,6 +100,51 @@ def train_case(R, variant, seed, batch_seed, num_items=None):
     }
 
 
+LOGIT_STRIDE = 97      # full-size cases keep every 97th logit (the full tensors are 8 MB)
+
+
+def mb_batch(vocab, behavior_tokens, n_items, rows, seed):
+    """train_MB_decoder-shaped batch (multi-behaviour sequences without sessions, tasks/train_MB_decoder.py:317-365):
+    rows of `n_items` items, each item = behaviour token + 4 code tokens, all rows full length."""
+    rng = np.random.default_rng(seed)
+    cat = syn.make_catalogue(20_000, 7)
+    ct = cat.tokens()
+    ids = np.empty((rows, n_items, 5), dtype=np.int64)
+    for r in range(rows):
+        it = rng.integers(0, cat.n_items, size=n_items)
+        ids[r, :, 1:] = ct[it]
+        ids[r, :, 0] = np.asarray(behavior_tokens)[rng.integers(0, len(behavior_tokens), size=n_items)]
+    ids = torch.from_numpy(ids.reshape(rows, n_items * 5))
+    labels = ids.clone()
+    for t in behavior_tokens:
+        labels[labels == t] = -100
+    return {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+
+
+def full_size_case(R, variant, seed, batch, max_his_len, vocab=1041, behavior_tokens=(526, 527, 528)):
+    """Whole-model parity at BASELINE.json's shapes (all layers of the packaged config, L = 5 (max_his_len + 1)): loss,
+    strided logits, gradient digests and the full embedding gradient of the unmodified reference."""
+    cfg = ref_shim.reference_config(variant, vocab_size=vocab, behavior_tokens=behavior_tokens, max_his_len=max_his_len,
+                                    model_max_length=max(1024, 5 * (max_his_len + 1)))
+    m, sd, shapes = build(R, variant, cfg, seed, "sdpa")
+    with torch.no_grad():
+        out = m(**batch)
+    m2, _, _ = build(R, variant, cfg, seed, "eager")
+    out2 = m2(**batch)
+    out2.loss.backward()
+    grads = [(k, (p.grad if p.grad is not None else torch.zeros_like(p))) for k, p in m2.named_parameters()
+             if k != "lm_head.weight"]
+    pub = cfg_public(cfg)
+    return {
+        "variant": variant, "config": pub, "weight_seed": seed, "weight_checksum": checksum(sd), "shapes": shapes,
+        "temperature": 0.7, "batch": batch, "num_items_in_batch": None,
+        "logits_stride": LOGIT_STRIDE, "logits_samples": out.logits.reshape(-1)[::LOGIT_STRIDE].clone(),
+        "logits_absmax": out.logits.abs().max().double(),
+        "loss": out.loss.double(), "loss_eager": out2.loss.detach().double(), "grads": grad_digest(grads),
+        "embed_grad": dict(grads)["model.embed_tokens.weight"].clone(),
+    }
+
+
 def decode_case(R, variant, seed, batch_seed, target_behavior, K):
     cfg = tiny_config(variant)
     cat = syn.make_catalogue(3000, 1)
@@ -151,6 +197,14 @@ def main():
         "train_qwen3sessionmoe.pt": lambda: train_case(R, "Qwen3SessionMoe", 44, 5),
         "train_qwen3sessionmulti.pt": lambda: train_case(R, "Qwen3SessionMulti", 45, 6),
         "train_qwen3moe.pt": lambda: train_case(R, "Qwen3Moe", 47, 8),
+        # BASELINE.json configs[1] shape (Qwen3Multi, 8 layers, max_his_len 100: L = 505, full-length rows)
+        "train_qwen3multi_headline.pt": lambda: full_size_case(
+            R, "Qwen3Multi", 48, syn.make_train_batch(syn.make_catalogue(50_000, 1234), 4, max_his_len=100, seed=11,
+                                                      full_length=True), 100),
+        # BASELINE.json configs[3] shape (train_MB_decoder: Qwen3Moe, 4 behaviour types, max_his_len 200: L = 1005)
+        "train_qwen3moe_mb4.pt": lambda: full_size_case(
+            R, "Qwen3Moe", 49, mb_batch(1042, (526, 527, 528, 1041), 201, 2, 12), 200, vocab=1042,
+            behavior_tokens=(526, 527, 528, 1041)),
         "decode_qwen3multi_lvl2.pt": lambda: decode_case(R, "Qwen3Multi", 42, 5, 2, 8),
         "decode_qwen3multi_lvl1.pt": lambda: decode_case(R, "Qwen3Multi", 46, 7, 1, 6),
     }

@@ -63,3 +63,27 @@ def test_ranking_metrics():
     met = od.metrics(hits, g["rank_targets"], g["rank_names"])
     for k, v in g["rank_metrics"].items():
         assert abs(met[k] - v) < 1e-12, k
+
+
+FULL_SIZE = ["train_qwen3multi_headline.pt", "train_qwen3moe_mb4.pt"]
+
+
+@pytest.mark.parametrize("name", FULL_SIZE)
+def test_full_size_forward_loss_grads(name):
+    """BASELINE.json's shapes (all 8 layers; L = 505 Qwen3Multi / L = 1005 four-behaviour Qwen3Moe): the oracle against
+    the unmodified reference's loss, strided logits, gradient digests and full embedding gradient."""
+    g = load_golden(name)
+    spec = spec_from_golden(g, g["temperature"])
+    W = weights_from_golden(g, requires_grad=True)
+    out = om.forward(spec, W, **g["batch"])
+    mine = out["logits"].reshape(-1)[::g["logits_stride"]]
+    assert torch.allclose(mine, g["logits_samples"], rtol=1e-4, atol=5e-5)
+    assert abs(out["loss"].item() - g["loss"].item()) < 1e-5 * max(1.0, abs(g["loss"].item()))
+    out["loss"].backward()
+    for k, d in g["grads"].items():
+        gr = W[k].grad if W[k].grad is not None else torch.zeros_like(W[k])
+        ref_norm = d["norm"].item()
+        assert abs(gr.norm().item() - ref_norm) <= 1e-4 * ref_norm + 1e-7, k
+        mine = gr.reshape(-1)[::d["stride"]][: d["samples"].numel()]
+        assert torch.allclose(mine, d["samples"], rtol=1e-3, atol=1e-5 * max(ref_norm, 1e-3)), k
+    assert torch.allclose(W["model.embed_tokens.weight"].grad, g["embed_grad"], rtol=1e-3, atol=1e-6)
