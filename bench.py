@@ -30,6 +30,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gamer", choices=["gamer", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "mb_decoder", "long_history"],
+                    help="train = the headline (BASELINE.json configs[1] + the configs[2] eval leg); mb_decoder = configs[3] "
+                         "(train_MB_decoder: Qwen3Moe, 4 behaviour types, max_his_len 200); long_history = configs[4] "
+                         "(Qwen3Multi max_his_len 500, batch sweep 256-4096)")
     ap.add_argument("--global-batch", type=int, default=1024)
     ap.add_argument("--micro-batch", type=int, default=512,
                     help="rows per forward+backward pass (gradient accumulation over the per-GPU batch); 512 rows keep "
@@ -312,6 +316,166 @@ def eval_leg(args, dev, world, rank, barrier):
     return obj
 
 
+def _roofline_of(name, top, step_ms, peaks):
+    tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if top["flops"] > 0:
+        ach, peak, unit, bound = top["flops"] / (top["ms"] / 1e3) / 1e12, tens_peak, "TFLOP/s", "tensor"
+    else:
+        ach, peak, unit, bound = top["bytes"] / (top["ms"] / 1e3) / 1e9, hbm_peak, "GB/s", "hbm"
+    return {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+            "share_of_step": top["ms"] / step_ms, "avg_launch_ms": top["ms"] / max(1, top["calls"])}
+
+
+def _breakdown_of(summ, peaks):
+    total = sum(v["ms"] for v in summ.values()) or 1.0
+    out = {"_note": "one untimed step with CUDA events around every entry point (adds launch gaps)"}
+    for n, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:12]:
+        e = {"ms_per_step": v["ms"], "share": v["ms"] / total, "calls_per_step": v["calls"]}
+        if v["flops"]:
+            e["tflops"] = v["flops"] / (v["ms"] / 1e3) / 1e12
+            e["frac_of_peak"] = e["tflops"] / peaks.get("bf16_tflops_sustained", 1400.0)
+        elif v["bytes"]:
+            e["gbs"] = v["bytes"] / (v["ms"] / 1e3) / 1e9
+            e["frac_of_peak"] = e["gbs"] / peaks.get("hbm_gbs", 6650.0)
+        out[n] = e
+    return out
+
+
+def run_secondary(args):
+    """`--workload mb_decoder` (BASELINE.json configs[3]) and `--workload long_history` (configs[4]): the same step
+    (forward + backward + all-reduce + clip + AdamW through NativeTrainer, bf16, dropout on, CUDA graphs) on the other two
+    training shapes, same JSON contract; long_history adds a global-batch sweep 256..4096 and the embedding-gather /
+    masked-attention rooflines at L = 2505."""
+    import torch
+    import torch.distributed as dist
+    from gamer_b200 import _cabi, modeling
+    from gamer_b200 import synthetic as syn
+    from gamer_b200.trainer import NativeTrainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cat = syn.make_catalogue(250_000, 1234)
+    torch.manual_seed(42)
+    if args.workload == "mb_decoder":
+        mhl, beh_tokens = 200, (526, 527, 528, 1041)
+        cfg = model_config(mhl, vocab=1042)
+        cfg.num_behavior = 4
+        cfg.behavior_maps = {str(t): i for i, t in enumerate(beh_tokens)}
+        model = modeling.Qwen3MoeWithTemperature(cfg)
+        batches, mb_rows = [args.global_batch if args.global_batch != 1024 else 512], 256
+        make = lambda rows, seed: syn.make_mb_batch(cat, rows, max_his_len=mhl, behavior_tokens=beh_tokens, seed=seed)
+        what = ("Qwen3Moe multi-behaviour decoder train (configs[3]: train_MB_decoder, 4 behaviour types, no sessions), "
+                f"max_his_len={mhl}")
+    else:
+        mhl = 500
+        cfg = model_config(mhl)
+        model = modeling.Qwen3MultiWithTemperature(cfg)
+        batches, mb_rows = [256, 512, 1024, 2048, 4096], 64
+        make = lambda rows, seed: syn.make_train_batch(cat, rows, max_his_len=mhl, seed=seed, full_length=True)
+        what = f"Qwen3Multi smb_explicit_decoder train, long-history stress (configs[4]), max_his_len={mhl}"
+    L = 5 * (mhl + 1)
+    model.set_hyper(0.7)
+    model = model.to(dev).train()
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    trainer = NativeTrainer(model, lr=5e-4, weight_decay=0.01, max_grad_norm=1.0, warmup_steps=2, total_steps=10_000)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sweep, line = [], None
+    for gb in batches:
+        assert gb % world == 0
+        B_local = gb // world
+        mb = min(mb_rows, B_local)
+        host = {k: v.pin_memory() for k, v in make(B_local, 1000 * rank + gb).items()}
+        resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        for _ in range(args.warmup):
+            trainer.step(resident, micro_batch=mb)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                trainer.step(resident, micro_batch=mb)
+            ev1.record()
+            barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / args.steps
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            loss = trainer.step({k: v.to(dev, non_blocking=True) for k, v in host.items()}, micro_batch=mb)
+            loss_host = float(loss.item())
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / args.steps
+        point = {"global_batch": gb, "micro_batch": mb, "ms_per_step": ms, "samples_per_s": gb / (ms / 1e3),
+                 "tokens_per_s": gb * L / (ms / 1e3), "e2e_samples_per_s": gb / (e2e_ms / 1e3)}
+        sweep.append(point)
+        if gb == batches[-1]:
+            # kernel breakdown + rooflines on one eager step of the last (largest) batch
+            graphs_on, trainer.use_cuda_graphs = trainer.use_cuda_graphs, False
+            prof = _cabi.Profile()
+            _cabi.set_profile(prof)
+            trainer.step(resident, micro_batch=mb)
+            barrier()
+            _cabi.set_profile(None)
+            trainer.use_cuda_graphs = graphs_on
+            summ = prof.summary()
+            name, top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+            line = {"metric": "train_samples_per_s", "value": point["samples_per_s"], "unit": "samples/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": f"{what}, L={L}, global batch {gb}, full-length rows, "
+                                           "fwd+bwd+allreduce+clip+AdamW", "global_batch": gb, "per_gpu_batch": B_local,
+                               "micro_batch": mb, "seq_len": L, "parallelism": f"dp{world}",
+                               "tokens_per_s": point["tokens_per_s"],
+                               "dropout": f"on (dropout_rate={cfg.dropout_rate}, attention_dropout={cfg.attention_dropout})",
+                               "l2_policy": "inputs and activations exceed the 126 MB L2; no flush needed"},
+                    "clocks": clocks.summary(), "gpu_launches": prof.launches * args.steps, "cuda_graphs": bool(graphs_on),
+                    "e2e": {"value": point["e2e_samples_per_s"], "unit": "samples/s",
+                            "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * world,
+                            "d2h_bytes_per_step": 4 * world, "last_loss": loss_host},
+                    "roofline": _roofline_of(name, top, ms, peaks), "kernel_breakdown": _breakdown_of(summ, peaks)}
+            if args.workload == "long_history":
+                line["sweep"] = sweep
+                # the two rooflines configs[4] names: embedding gather (HBM) and masked attention (tensor) at L = 2505
+                for key, label in (("gamer_embed_route_fwd", "embedding_gather"), ("gamer_embed_bwd", "embedding_grad"),
+                                   ("gamer_attn_fwd", "masked_attention_fwd"), ("gamer_attn_bwd", "masked_attention_bwd")):
+                    if key in summ:
+                        line.setdefault("rooflines", {})[label] = _roofline_of(key, summ[key], ms, peaks)
+        del resident, host
+        torch.cuda.empty_cache()
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -374,6 +538,9 @@ def main():
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload != "train":
+        run_secondary(args)
         return
     import torch
     import torch.distributed as dist
@@ -465,11 +632,27 @@ def main():
     launches = launches_per_step * args.steps     # the graph replays the same kernels the eager step launches
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D of inputs + D2H of the loss) ------
+    # The step's inputs are the pre-tokenised rows of the input pipeline (collate.PackedSessions in pinned host memory:
+    # 4 code ids + behaviour + session per interaction, 2.3 MB per 1024 rows instead of 24.8 MB of padded int64 tensors);
+    # they are copied to the device and expanded there by collate_train into the six [B, L] tensors the model takes.
+    from gamer_b200 import collate
+    stores = [collate.PackedSessions.from_histories(
+        syn.train_histories(cat, B_local, max_his_len=args.max_his_len, seed=1000 * rank + i, full_length=True)).pin_memory()
+        for i in range(n_host)]
+    h2d_bytes = stores[0].nbytes()
+    all_rows = torch.arange(B_local, device=dev)
+
+    def e2e_batch(i):
+        st = stores[i % n_host].to(dev, non_blocking=True)
+        return collate.collate_train(st, all_rows, args.max_his_len, syn.BEHAVIOR_TOKENS, syn.BEHAVIOR_LEVEL, pad=syn.PAD,
+                                     width=args.max_his_len + 1)
+
+    chk = e2e_batch(0)                                       # the device collate reproduces the resident batch bit for bit
+    assert all(torch.equal(chk[k], resident[0][k]) for k in resident[0]), "device collate differs from the synthetic batch"
     barrier()
     ev0.record()
     for i in range(args.steps):
-        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_host].items()}
-        loss = trainer.step(b, micro_batch=mb)
+        loss = trainer.step(e2e_batch(i), micro_batch=mb)
         loss_host = float(loss.item())
     ev1.record()
     barrier()

@@ -43,6 +43,9 @@ class PackedSessions:
         return PackedSessions(*(t.to(device, non_blocking=non_blocking) for t in
                                 (self.item_tokens, self.behavior, self.session, self.offsets)))
 
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.item_tokens, self.behavior, self.session, self.offsets))
+
     def pin_memory(self) -> "PackedSessions":
         return PackedSessions(*(t.pin_memory() for t in (self.item_tokens, self.behavior, self.session, self.offsets)))
 
@@ -58,11 +61,13 @@ class PackedSessions:
         return PackedSessions(torch.cat(toks), torch.cat(beh), torch.cat(sess), torch.tensor(off, dtype=torch.int64))
 
 
-def _window(store: PackedSessions, users: torch.Tensor, n_max: int, left_pad: bool):
-    """Gather the last <= n_max interactions of every user into [B, n] grids.  Returns (row index grid, valid mask)."""
+def _window(store: PackedSessions, users: torch.Tensor, n_max: int, left_pad: bool, width: int | None = None):
+    """Gather the last <= n_max interactions of every user into [B, n] grids.  Returns (row index grid, valid mask).
+    `width` (items per row of the grid) defaults to the longest kept history, which costs one host sync; callers that
+    know it (fixed-shape batches for CUDA-graph replay) pass it."""
     start, end = store.offsets[users], store.offsets[users + 1]
     n = torch.clamp(end - start, max=n_max)                                    # items kept per user
-    width = int(n.max())
+    width = int(n.max()) if width is None else int(width)
     t = torch.arange(width, device=users.device).unsqueeze(0)                  # [1, width]
     if left_pad:
         valid = t >= (width - n).unsqueeze(1)
@@ -98,10 +103,11 @@ def _expand(store, idx, valid, behavior_tokens, behavior_level, pad):
     return {k: v.reshape(B, n * TOKENS_PER_ITEM).contiguous() for k, v in out.items()}
 
 
-def collate_train(store: PackedSessions, users, max_his_len: int, behavior_tokens, behavior_level, pad: int = 4) -> dict:
+def collate_train(store: PackedSessions, users, max_his_len: int, behavior_tokens, behavior_level, pad: int = 4,
+                  width: int | None = None) -> dict:
     """DecoderOnlyCollator (train split, only_train_response=False): the last max_his_len + 1 items, right-padded."""
     users = torch.as_tensor(users, dtype=torch.int64, device=store.offsets.device)
-    idx, valid = _window(store, users, max_his_len + 1, left_pad=False)
+    idx, valid = _window(store, users, max_his_len + 1, left_pad=False, width=width)
     out = _expand(store, idx, valid, behavior_tokens, behavior_level, pad)
     labels = out["input_ids"].clone()
     ignore = labels == pad
@@ -112,11 +118,11 @@ def collate_train(store: PackedSessions, users, max_his_len: int, behavior_token
 
 
 def collate_eval(store: PackedSessions, users, max_his_len: int, target_behavior: int, behavior_tokens, behavior_level,
-                 pad: int = 4) -> dict:
+                 pad: int = 4, width: int | None = None) -> dict:
     """DecoderOnlyTestCollator + the target-behaviour append of test_SMB_decoder.py:105-117: the last max_his_len items,
     LEFT-padded, then one more column holding the target behaviour token (session max+1, extended max+1, its level)."""
     users = torch.as_tensor(users, dtype=torch.int64, device=store.offsets.device)
-    idx, valid = _window(store, users, max_his_len, left_pad=True)
+    idx, valid = _window(store, users, max_his_len, left_pad=True, width=width)
     out = _expand(store, idx, valid, behavior_tokens, behavior_level, pad)
     B = users.numel()
     dev = users.device

@@ -114,6 +114,10 @@ class _GamerCausalLM(PreTrainedModel):
         if getattr(config, "mlp_type", None) != "Qwen3":
             raise NotImplementedError("gamer_b200 implements mlp_type='Qwen3' (MyQwen3SparseMLP); the PBATransformer "
                                       "FFN variant is outside the hot path (SURVEY.md §8)")
+        if getattr(config, "Moe_behavior_only", False):
+            # Qwen3Multi/router.py:31-48: two experts only (behaviour token vs code tokens); the packaged configs and both
+            # SMB tasks run with False.  Silently using the per-position routing instead would train a different model.
+            raise NotImplementedError("gamer_b200 implements the per-position expert routing (Moe_behavior_only=False)")
         super().__init__(config)
         self.model = _Backbone(config, self.VARIANT)
         self.vocab_size = config.vocab_size

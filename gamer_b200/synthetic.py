@@ -94,6 +94,21 @@ def _hist_len(rng, max_items, full_length, median=60.0):
     return min(n, max_items)
 
 
+def train_histories(cat: Catalogue, batch: int, max_his_len: int = 100, seed: int = 0, full_length: bool = False,
+                    median_len: float = 60.0) -> list:
+    """The raw histories behind `make_train_batch(same arguments)` — (item tokens [n, 4], behaviour [n], session [n]) per
+    row, same RNG draws — i.e. the rows of a `collate.PackedSessions` store whose `collate_train` output IS that batch."""
+    rng = np.random.default_rng(seed)
+    ct = cat.tokens()
+    out = []
+    for _ in range(batch):
+        n = _hist_len(rng, max_his_len + 1, full_length, median_len)
+        items, beh, sess = _user_history(rng, cat, n)
+        beh[-1] = N_BEHAVIOR - 1 if rng.random() < 0.5 else beh[-1]
+        out.append((ct[items], beh, sess))
+    return out
+
+
 def make_train_batch(cat: Catalogue, batch: int, max_his_len: int = 100, seed: int = 0,
                      full_length: bool = False, median_len: float = 60.0) -> dict:
     """DecoderOnlyCollator-shaped training batch (right padding).  int64 CPU tensors."""
@@ -178,3 +193,24 @@ def seeded_state_dict(shapes: dict, seed: int = 42, std: float = 0.05, norm_jitt
         else:
             out[k] = std * torch.randn(shp, generator=g)
     return out
+
+
+def make_mb_batch(cat: Catalogue, batch: int, max_his_len: int = 200, behavior_tokens=(526, 527, 528, 1041),
+                  seed: int = 0) -> dict:
+    """train_MB_decoder-shaped batch (multi-behaviour sequences WITHOUT sessions, tasks/train_MB_decoder.py:317-365;
+    BASELINE.json configs[3]: four behaviour types): rows of max_his_len + 1 items, item = behaviour token + 4 code
+    tokens, all rows full length; labels mask the behaviour tokens.  int64 CPU tensors."""
+    rng = np.random.default_rng(seed)
+    ct = cat.tokens()
+    n = max_his_len + 1
+    ids = np.empty((batch, n, TOKENS_PER_ITEM), dtype=np.int64)
+    for r in range(batch):
+        u = rng.random(n)
+        ranks = np.minimum((cat.n_items ** u).astype(np.int64), cat.n_items - 1)
+        ids[r, :, 1:] = ct[ranks]
+        ids[r, :, 0] = np.asarray(behavior_tokens)[rng.integers(0, len(behavior_tokens), size=n)]
+    ids = torch.from_numpy(ids.reshape(batch, n * TOKENS_PER_ITEM))
+    labels = ids.clone()
+    for t in behavior_tokens:
+        labels[labels == t] = -100
+    return {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}

@@ -5,10 +5,15 @@ Scope (SURVEY.md §8(b) "CLI" row): the flags, the model construction (config mu
 `set_hyper`, `resize_token_embeddings`), the optimisation recipe (AdamW, cosine schedule with warm-up ratio, gradient
 accumulation with `num_items_in_batch` normalisation, per-epoch validation loss, best-checkpoint saving, patience) and
 the evaluation loop (per-behaviour candidate trie, constrained beam search, hit/recall/ndcg, merged result, results
-JSON) are the reference's.  The reference's dataset machinery (string prompts + HF tokenizer over Git-LFS JSON files) is
-out of scope: inputs here are the ShortVideoAD-shaped synthetic sessions of
-`gamer_b200.synthetic`, produced directly as the tensors the reference's collators emit.  HF `Trainer` (needs
-`accelerate`) is replaced by `gamer_b200.trainer.NativeTrainer`.
+JSON) are the reference's.
+
+Input pipeline: when `<data_path>/<dataset>/` holds the reference's files
+(`<dataset>.SMB.{inter,behavior,session}.json`, the index file, `<dataset>.behavior_level.json`) they are loaded by
+`gamer_b200.dataset` — token ids, session splits, the `smb_explicit_decoder_<k>` k-fold augmentation and the candidate
+trie exactly as the reference builds them (tests/test_dataset_cpu.py) — otherwise a ShortVideoAD-shaped synthetic corpus
+of the same form is generated.  Either way the corpus is a pre-tokenised `PackedSessions` store resident on the GPU and
+every batch is assembled there by `gamer_b200.collate` (no strings, no tokenizer, ~7 B per interaction of H2D once).
+HF `Trainer` (needs `accelerate`) is replaced by `gamer_b200.trainer.NativeTrainer`.
 """
 from __future__ import annotations
 
@@ -20,6 +25,8 @@ import time
 import torch
 import torch.distributed as dist
 
+from . import collate
+from . import dataset as ds
 from . import modeling
 from . import synthetic as syn
 from .distributed import reduce_metric_sums, shard_range, world_info
@@ -52,28 +59,51 @@ def _info(msg):
         print(f"[gamer_b200] {msg}", flush=True)
 
 
-def _config(base_model: str, max_his_len: int, model_max_length: int):
-    """The runtime mutations of train_SMB_decoder.py:321-360 for the synthetic vocabulary (14 stub ids + 4 x 256 codes +
-    3 behaviour tokens = 1041, `synthetic.py`)."""
+def _corpus(data_path, dataset, index_file, max_his_len, synthetic_users, synthetic_items, seed) -> ds.SMBData:
+    root = os.path.join(data_path or "", dataset or "")
+    if data_path and dataset and os.path.exists(os.path.join(root, dataset + ".SMB.inter.json")):
+        data = ds.load_smb_files(data_path, dataset, index_file or ".index.json")
+        _info(f"dataset {dataset!r}: {len(data.users)} users, {data.catalogue.shape[0]} items, vocabulary {data.vocab_size} "
+              f"from {root}")
+        return data
+    _info(f"dataset {dataset!r}: no data files under {root!r} — ShortVideoAD-shaped synthetic corpus "
+          f"({synthetic_users} users, {synthetic_items} items, max_his_len={max_his_len})")
+    return ds.synthetic_corpus(synthetic_users, synthetic_items, max_his_len + 8, seed=seed)
+
+
+def _augment_of(tasks: str):
+    """loading_SMB.py:39-54: `smb_explicit_decoder` -> no augmentation, `smb_explicit_decoder_<k>` -> augment = k."""
+    t = (tasks or "smb_explicit_decoder").split(",")[0].lower()
+    if not t.startswith("smb_explicit_decoder"):
+        raise NotImplementedError(f"task {tasks!r}: the B200 hot path implements smb_explicit_decoder[_<k>]")
+    return None if t == "smb_explicit_decoder" else int(t.split("_")[3])
+
+
+def _config(base_model: str, max_his_len: int, model_max_length: int, data: ds.SMBData):
+    """The runtime mutations of train_SMB_decoder.py:321-360 for the corpus' vocabulary (14 base ids + the sorted added
+    tokens: 4 x 256 codes + the behaviour tokens = 1041 for three behaviours)."""
     from transformers.models.qwen3_moe import Qwen3MoeConfig
     cfg = Qwen3MoeConfig.from_pretrained(base_model)
-    cfg.vocab_size = syn.VOCAB
-    cfg.num_behavior = syn.N_BEHAVIOR
-    cfg.behavior_maps = {str(t): i for i, t in enumerate(syn.BEHAVIOR_TOKENS)}
+    tpi = data.catalogue.shape[1] + 1
+    cfg.vocab_size = data.vocab_size
+    cfg.num_behavior = len(data.behavior_tokens)
+    cfg.behavior_maps = {str(t): i for i, t in enumerate(data.behavior_tokens)}
     cfg.use_behavior_token = True
-    cfg.num_positions = syn.TOKENS_PER_ITEM
-    cfg.num_experts = syn.TOKENS_PER_ITEM + 1
+    cfg.num_positions = tpi
+    cfg.num_experts = tpi + 1
     cfg.n_positions = max_his_len + 1
     cfg.use_user_token = False
-    cfg.model_max_length = max(model_max_length, syn.TOKENS_PER_ITEM * (max_his_len + 1))
+    cfg.model_max_length = max(model_max_length, tpi * (max_his_len + 1))
     return cfg
 
 
-def _batches(cat, n_rows, batch, max_his_len, seed):
-    out = []
-    for i, b0 in enumerate(range(0, n_rows, batch)):
-        out.append(syn.make_train_batch(cat, min(batch, n_rows - b0), max_his_len=max_his_len, seed=seed + i))
-    return out
+def _step_users(n_rows: int, rows_per_step: int, epoch_seed: int):
+    """Shuffled user order of one epoch cut into optimizer steps of equal size (the ragged tail is dropped, as
+    DistributedSampler(drop_last) would): every rank runs the same number of steps with the same batch sizes."""
+    g = torch.Generator().manual_seed(epoch_seed)
+    perm = torch.randperm(n_rows, generator=g)
+    n_steps = n_rows // rows_per_step
+    return [perm[i * rows_per_step:(i + 1) * rows_per_step] for i in range(n_steps)]
 
 
 _PAD_VALUE = {"input_ids": syn.PAD, "attention_mask": 0, "labels": -100, "actions": 100, "session_ids": 0,
@@ -95,10 +125,16 @@ def _pad_to_common_length(batch, dev):
 
 
 @torch.no_grad()
-def _valid_loss(model, batches, dev):
-    """`--valid_loss` / per-epoch evaluation: mean of the per-batch losses (test_SMB_decoder.py:306-322)."""
+def _valid_loss(model, store, rank, world, batch_size, max_his_len, data):
+    """`--valid_loss` / per-epoch evaluation: mean of the per-batch losses (test_SMB_decoder.py:306-322) over this rank's
+    exact shard of the validation samples, batches collated on the device."""
     model.eval()
-    losses = [float(model(**{k: v.to(dev) for k, v in b.items()}).loss) for b in batches]
+    lo, hi = shard_range(store.n_users, rank, world)
+    losses = []
+    for b0 in range(lo, hi, batch_size):
+        users = torch.arange(b0, min(hi, b0 + batch_size), device=store.offsets.device)
+        b = collate.collate_train(store, users, max_his_len, data.behavior_tokens, data.behavior_level)
+        losses.append(float(model(**b).loss))
     model.train()
     return sum(losses) / max(1, len(losses))
 
@@ -115,9 +151,9 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
         raise ValueError(f"backbone {backbone!r}: the B200 hot path implements {sorted(BACKBONES)}")
     if optim != "adamw_torch" or lr_scheduler_type != "cosine":
         raise NotImplementedError("the native loop implements the reference recipe: adamw_torch + cosine schedule")
-    _info(f"dataset {dataset!r}: the reference's JSON/tokenizer pipeline is out of scope — training on ShortVideoAD-shaped "
-          f"synthetic sessions ({synthetic_users} users, {synthetic_items} items, max_his_len={max_his_len}); bf16 kernels")
-    cfg = _config(base_model, max_his_len, model_max_length)
+    data = _corpus(data_path, dataset, index_file, max_his_len, synthetic_users, synthetic_items, seed)
+    augment = _augment_of(tasks)
+    cfg = _config(base_model, max_his_len, model_max_length, data)
     model = BACKBONES[backbone].from_pretrained(resume_from_checkpoint) if resume_from_checkpoint else BACKBONES[backbone](cfg)
     model.set_hyper(temperature)
     model.resize_token_embeddings(cfg.vocab_size)
@@ -125,14 +161,15 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
-    cat = syn.make_catalogue(synthetic_items, 1234)
-    # equal rows per rank (the remainder of an uneven split is dropped, as DistributedSampler(drop_last) would): every
-    # rank then runs the same number of optimizer steps with the same batch sizes — and so the same NCCL sequence
-    n_rows = synthetic_users // world
+    # the whole corpus lives on the GPU as flat int arrays (pinned host copy -> one H2D); batches are collated there
+    train = ds.train_store(data, augment).pin_memory().to(dev, non_blocking=True)
+    valid = ds.valid_store(data).pin_memory().to(dev, non_blocking=True)
+    _info(f"train sequences {train.n_users} (augment={augment}), validation samples {valid.n_users}")
     step_rows = per_device_batch_size * gradient_accumulation_steps
-    train = _batches(cat, n_rows, step_rows, max_his_len, seed=10_000 * (rank + 1))
-    valid = _batches(cat, max(per_device_batch_size, n_rows // 8), per_device_batch_size, max_his_len, seed=777_000 + rank)
-    total_steps = epochs * len(train)
+    steps_per_epoch = train.n_users // (step_rows * world)
+    if steps_per_epoch == 0:
+        raise ValueError(f"{train.n_users} training sequences do not fill one optimizer step of {step_rows * world} rows")
+    total_steps = epochs * steps_per_epoch
     trainer = NativeTrainer(model, lr=learning_rate, weight_decay=weight_decay, max_grad_norm=1.0,
                             warmup_steps=int(math.ceil(warmup_ratio * total_steps)), total_steps=total_steps)
     if rank == 0:
@@ -142,8 +179,10 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
     best, bad, step = float("inf"), 0, 0
     for epoch in range(epochs):
         t0, seen = time.time(), 0
-        for b in train:
-            b = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+        # one global shuffle per epoch (same on every rank), rank r takes rows r::world of every step
+        for users in _step_users(train.n_users, step_rows * world, seed * 1000 + epoch):
+            mine = users[rank::world].to(dev)
+            b = collate.collate_train(train, mine, max_his_len, data.behavior_tokens, data.behavior_level)
             if world > 1:
                 b = _pad_to_common_length(b, dev)
             loss = trainer.step(b, micro_batch=per_device_batch_size)
@@ -153,7 +192,7 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
                 _info(f"epoch {epoch} step {step}/{total_steps} loss {float(loss):.4f} lr {trainer.current_lr():.2e}")
         torch.cuda.synchronize()
         dt = time.time() - t0
-        vl = torch.tensor([_valid_loss(model, valid, dev)], device=dev)
+        vl = torch.tensor([_valid_loss(model, valid, rank, world, per_device_batch_size, max_his_len, data)], device=dev)
         if world > 1:
             dist.all_reduce(vl)
             vl /= world
@@ -183,33 +222,43 @@ def test_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, d
     if backbone not in BACKBONES:
         raise ValueError(f"backbone {backbone!r}: the B200 hot path implements {sorted(BACKBONES)}")
     model = BACKBONES[backbone].from_pretrained(ckpt_path).to(dev).eval()
-    cat = syn.make_catalogue(synthetic_items, 1234)
+    data = _corpus(data_path, dataset, index_file, max_his_len, synthetic_users, synthetic_items, seed)
+    if model.config.vocab_size != data.vocab_size:
+        raise ValueError(f"checkpoint vocabulary {model.config.vocab_size} != data vocabulary {data.vocab_size}")
     metric_list = metrics.split(",")
-    names = [f"behavior_{i}" for i in range(syn.N_BEHAVIOR)]
+    names = list(data.behavior_names)
     wanted = names if not behaviors else [b for b in behaviors if b in names]
     if valid_loss:
-        batches = _batches(cat, max(test_batch_size, synthetic_users // 8), test_batch_size, max_his_len, seed=777_000 + rank)
-        vl = _valid_loss(model, batches, dev)
+        valid = ds.valid_store(data).pin_memory().to(dev, non_blocking=True)
+        vl = _valid_loss(model, valid, rank, world, test_batch_size, max_his_len, data)
         _info(f"Validation loss: {vl:.4f}")
         return vl
+    mode = "valid" if (test_task or "").lower().startswith("smb_valid") else "test"
+    store, targets_all = ds.eval_store(data, mode)
+    store = store.pin_memory().to(dev, non_blocking=True)
+    S = data.catalogue.shape[1]
     results, merged, total_all = [], {m: 0.0 for m in metric_list}, 0
     for beh_name in wanted:
         beh = names.index(beh_name)
-        items = cat.item_sequences(beh)
+        # the candidate trie of this behaviour: behaviour token + the code tokens of every catalogue item
+        # (test_SMB_decoder.py:467-501); users without a target of this behaviour are skipped (:123-135)
+        items = data.item_sequences(beh)
         fn = prefix_allowed_tokens_fn_by_last_token(flat_from_array(items), set(int(t) for t in items[:, -1]) | {syn.PAD})
-        lo, hi = shard_range(synthetic_users, rank, world)      # exact sharding: no duplicated users (quirk Q12)
+        users_b = [u for u in range(store.n_users) if beh in targets_all[u]]
+        lo, hi = shard_range(len(users_b), rank, world)         # exact sharding: no duplicated users (quirk Q12)
         sums, count = {m: 0.0 for m in metric_list}, 0
         for b0 in range(lo, hi, test_batch_size):
-            n = min(test_batch_size, hi - b0)
-            batch, targets = syn.make_eval_batch(cat, n, max_his_len=max_his_len, target_behavior=beh, seed=seed * 1000 + b0)
-            out = model.generate(**{k: v.to(dev) for k, v in batch.items()}, max_new_tokens=syn.TOKENS_PER_ITEM - 1,
-                                 prefix_allowed_tokens_fn=fn, num_beams=num_beams, num_return_sequences=num_beams,
-                                 output_scores=True, return_dict_in_generate=True, early_stopping=True)
+            sel = users_b[b0:min(hi, b0 + test_batch_size)]
+            n = len(sel)
+            batch = collate.collate_eval(store, torch.tensor(sel, device=dev), max_his_len, beh, data.behavior_tokens,
+                                         data.behavior_level)
+            out = model.generate(**batch, max_new_tokens=S, prefix_allowed_tokens_fn=fn, num_beams=num_beams,
+                                 num_return_sequences=num_beams, output_scores=True, return_dict_in_generate=True,
+                                 early_stopping=True)
             # hit matching and metric sums on the device, on the code-id tuples themselves (ranking.py: the tensor form is
             # checked against the string functions of the reference in tests/test_ranking_device_cpu.py)
-            S = syn.TOKENS_PER_ITEM - 1
-            gen = out.sequences[:, -S:].view(n, num_beams, S)
-            tt, cnt = pack_targets(targets, S, device=dev)
+            gen = out.generated.view(n, num_beams, S)
+            tt, cnt = pack_targets([targets_all[u][beh] for u in sel], S, device=dev)
             res = metric_sums(topk_hits(gen, tt), cnt, metric_list)
             for m in metric_list:
                 sums[m] = sums[m] + res[m]

@@ -79,3 +79,14 @@ def test_ranking_matches_reference_golden():
     met = ranking.get_metrics_results(hits, g["rank_names"], g["rank_targets"])
     for k, v in g["rank_metrics"].items():
         assert abs(met[k] - v) < 1e-12, k
+
+
+def test_moe_behavior_only_is_rejected():
+    """Qwen3Multi/router.py:31-48: the two-expert routing is not implemented; it must not be silently replaced."""
+    import pytest
+    from transformers.models.qwen3_moe import Qwen3MoeConfig
+    from gamer_b200 import modeling
+    cfg = Qwen3MoeConfig.from_pretrained(os.path.join(ROOT, "config", "s2s-models", "Qwen3Multi"))
+    cfg.num_positions, cfg.model_max_length, cfg.Moe_behavior_only = 5, 1024, True
+    with pytest.raises(NotImplementedError):
+        modeling.Qwen3MultiWithTemperature(cfg)
