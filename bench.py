@@ -472,6 +472,7 @@ def run_secondary(args):
     if rank == 0:
         emit(line)
     if world > 1:
+        trainer.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -663,6 +664,7 @@ def main():
 
     eval_obj = None
     graphs_flag = bool(trainer.use_cuda_graphs)
+    trainer.close()                                          # graphs that hold NCCL kernels go before the process group
     if not args.no_eval:
         del trainer, resident
         torch.cuda.empty_cache()

@@ -208,6 +208,7 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
                 _info(f"early stop after {patience} evaluations without improvement")
                 break
     _info(f"best eval_loss {best:.4f}; checkpoint in {output_dir}")
+    trainer.close()
     if world > 1:
         dist.barrier()
     return best

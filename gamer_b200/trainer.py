@@ -14,7 +14,8 @@ loop underneath it, restated B200-first:
   * the forward + backward of a micro-batch (~1500 kernel launches, ~11 us of Python/ctypes each) is captured ONCE per
     batch shape into a CUDA graph and replayed: inputs are copied into static buffers, every operand (flat weights,
     transposed copies, gradient buffer) keeps its address, and the dropout masks change per replay through a device-side
-    offset word.  With graphs the gradient all-reduce is launched after the last micro-batch's replay.
+    offset word.  The graph of a step's last micro-batch also holds the per-layer bucket all-reduces (NCCL's stream as a
+    parallel branch), so the overlap with the backward survives the capture.
 """
 from __future__ import annotations
 
@@ -140,14 +141,18 @@ class NativeTrainer:
         one = torch.ones((), dtype=torch.float32, device=self.dev)
         return E.loss_backward(a, self.pack, st, one, self.G, on_layer_done=hook)
 
-    def _graph_key(self, batch):
+    def _graph_key(self, batch, reduce):
         cfg = self.model._drop_config()
         return (tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self.BATCH_KEYS if batch.get(k) is not None),
-                cfg[1:] if cfg else None, float(self.model.temperature))
+                cfg[1:] if cfg else None, float(self.model.temperature), bool(reduce))
 
-    def _capture(self, key, batch, inv_norm):
+    def _capture(self, key, batch, inv_norm, reduce):
         """Capture forward + backward of one micro-batch shape.  The eager run that precedes every capture (see
-        forward_backward) has already initialised the lazily configured kernels."""
+        forward_backward) has already initialised the lazily configured kernels.  With `reduce` (the last micro-batch of a
+        step on more than one rank) the per-layer bucket all-reduces are captured too: each is launched from the backward
+        hook on NCCL's stream — a parallel branch of the graph that runs beside the remaining backward kernels, as DDP's
+        bucketed all-reduce does for the reference (tasks/train_SMB_decoder.py:396-428) — and joined before the capture
+        ends."""
         static = {k: torch.empty_like(batch[k]) for k in self.BATCH_KEYS if batch.get(k) is not None}
         for k, v in static.items():
             v.copy_(batch[k])
@@ -156,7 +161,9 @@ class NativeTrainer:
         torch.cuda.synchronize()
         torch.cuda.empty_cache()     # hand the eager run's cached activations back: the graph gets its own pool
         with torch.cuda.graph(g):
-            loss = self._run_micro(static, s_inv, None)
+            loss = self._run_micro(static, s_inv, self._bucket_hook if reduce else None)
+            if reduce:
+                self.reducer.wait_all()
         if len(self.graphs) >= self.max_graphs:
             self.graphs.pop(next(iter(self.graphs)))
         self.graphs[key] = (g, static, s_inv, loss)
@@ -168,26 +175,31 @@ class NativeTrainer:
         self.micro_batches += 1
         if not self.use_cuda_graphs:
             return self._run_micro(batch, inv_norm, self._bucket_hook if last_micro else None)
-        key = self._graph_key(batch)
+        reduce = last_micro and self.world > 1
+        key = self._graph_key(batch, reduce)
         entry = self.graphs.get(key)
         if entry is None:
             self.seen[key] = self.seen.get(key, 0) + 1
             if self.seen[key] < 2:                 # first occurrence of a shape: eager (also the kernels' warm-up)
-                # same collective as the replays (one flat all-reduce), so ranks whose graph caches differ — ragged
-                # batches give every rank its own shape history — still issue identical NCCL sequences
-                loss = self._run_micro(batch, inv_norm, None)
-                if last_micro:
-                    self.reducer.launch_flat()
-                return loss
-            entry = self._capture(key, batch, inv_norm)      # capture records, it does not execute
+                # same collectives as the replays (the per-layer buckets, in backward order), so ranks whose graph caches
+                # differ — ragged batches give every rank its own shape history — still issue identical NCCL sequences
+                return self._run_micro(batch, inv_norm, self._bucket_hook if reduce else None)
+            entry = self._capture(key, batch, inv_norm, reduce)      # capture records, it does not execute
         g, static, s_inv, loss = entry
         for k, v in static.items():
             v.copy_(batch[k], non_blocking=True)
         s_inv.copy_(inv_norm)
-        g.replay()
-        if last_micro:
-            self.reducer.launch_flat()             # one all-reduce over the whole flat gradient buffer
+        g.replay()                                 # (with `reduce`: the bucket all-reduces are part of the graph)
         return loss.clone()
+
+    def close(self):
+        """Drop the captured graphs.  Graphs that hold NCCL kernels keep the communicator busy: call this (or delete the
+        trainer) before `dist.destroy_process_group()`, which otherwise waits on them forever."""
+        self.graphs.clear()
+        self.opt_graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
 
     def step(self, batch, micro_batch=None):
         """One optimizer step over `batch` (device tensors, [B, L]); `micro_batch` splits it for gradient accumulation

@@ -24,6 +24,8 @@ def _grad_of(trainer, batch, E):
 
 
 def _worker(rank, world, port, ret):
+    import faulthandler
+    faulthandler.dump_traceback_later(90, exit=True)      # a collective that never completes must not hang the box
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -37,12 +39,13 @@ def _worker(rank, world, port, ret):
         # full-length rows: every rank normalises by the same label count, so mean-of-rank-means = global mean
         full = syn.make_train_batch(cat, 8, max_his_len=12, seed=5, full_length=True)
         dev = torch.device("cuda", rank)
-        res = {}
+        res, trainers = {}, []
         for graphs in (False, True):
             m = build_model(g).to(dev).train()
             m.config.dropout_rate = 0.0
             m.config.attention_dropout = 0.0
             tr = NativeTrainer(m, use_cuda_graphs=graphs)
+            trainers.append(tr)
             half = {k: v[rank * 4:(rank + 1) * 4].to(dev) for k, v in full.items()}
             reps = 3 if graphs else 1            # graphs: eager, capture + replay, replay
             for _ in range(reps):
@@ -60,6 +63,8 @@ def _worker(rank, world, port, ret):
             rel = ((res[True] - whole).norm() / whole.norm()).item()
             ret["rel"] = rel
             ret["max"] = ((res[True] - whole).abs().max() / whole.abs().max()).item()
+        for t in trainers:          # graphs holding NCCL kernels must go before the process group does
+            t.close()
     finally:
         dist.destroy_process_group()
 
