@@ -310,6 +310,18 @@ def eval_leg(args, dev, world, rank, barrier):
         obj["roofline"] = {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                            "traffic": None, "share_of_call": top["ms"] / total, "avg_launch_ms": top["ms"] / max(1, top["calls"]),
                            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
+            if tr and users == 256 and world == 1:
+                obj["roofline"]["traffic"] = tr["bytes_per_launch"]
+                obj["roofline"]["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
+                obj["roofline"]["traffic_source"] = tr["source"]
+        except Exception:
+            pass
+        if "gamer_attn_decode" in summ and name != "gamer_attn_decode":       # the decode-specific kernel, beside the dominant one
+            d = summ["gamer_attn_decode"]
+            obj["decode_attention"] = {"tflops": d["flops"] / (d["ms"] / 1e3) / 1e12, "gbs": d["bytes"] / (d["ms"] / 1e3) / 1e9,
+                                       "avg_launch_ms": d["ms"] / max(1, d["calls"]), "share_of_call": d["ms"] / total}
         obj["kernel_breakdown"] = {k: {"ms_per_call": v["ms"], "share": v["ms"] / total, "launches": v["calls"]}
                                    for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:10]}
         obj["gpu_launches_per_call"] = prof.launches
@@ -691,7 +703,7 @@ def main():
                     "frac": ach / hbm_peak, "traffic": None}
         try:   # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
-            if tr:
+            if tr and mb == 512:                 # the captures were taken at the default micro-batch (512 rows)
                 roof["traffic"] = tr["bytes_per_launch"]
                 roof["traffic_unit"] = "bytes/launch"
                 roof["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
@@ -706,14 +718,35 @@ def main():
                         "which single kernels cannot be timed)")
         kern = sorted(breakdown_all.items(), key=lambda kv: -kv[1]["ms"])
         total_kernel_ms = sum(v["ms"] for _, v in kern) or 1.0
-        breakdown = {"_note": "one untimed step with CUDA events around every entry point (adds launch gaps)"}
+        breakdown = {"_note": "one untimed step with CUDA events around every entry point (adds launch gaps); attention "
+                              "FLOPs are counted on the causal pair count, backward = 2.5 x forward (five GEMMs: S recompute, "
+                              "dP, dV, dK, dQ) — multiply gamer_attn_bwd's tflops by 0.8 for SURVEY 8(d)'s 2 x forward convention"}
         for n, v in kern[:12]:
             e = {"ms_per_step": v["ms"], "share": v["ms"] / total_kernel_ms, "calls_per_step": v["calls"]}
             if v["flops"]:
                 e["tflops"] = v["flops"] / (v["ms"] / 1e3) / 1e12
+                e["frac_of_peak"] = e["tflops"] / tens_peak
             elif v["bytes"]:
                 e["gbs"] = v["bytes"] / (v["ms"] / 1e3) / 1e9
+                e["frac_of_peak"] = e["gbs"] / hbm_peak
             breakdown[n] = e
+        # the other kernels the north star names a roofline target for, each with its like-for-like DRAM traffic when a
+        # capture at this micro-batch is committed (profiles/ncu_traffic.json)
+        rooflines = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            traffic = {}
+        for n in ("gamer_gemm_bf16_tn", "gamer_gemm_bf16_wgrad", "gamer_attn_fwd", "gamer_attn_bwd", "gamer_embed_route_fwd",
+                  "gamer_embed_bwd"):
+            if n in breakdown_all and breakdown_all[n]["ms"] > 0:
+                r = _roofline_of(n, breakdown_all[n], step_ms, peaks)
+                tr = traffic.get(n)
+                if tr and mb == 512:
+                    r["traffic"] = tr["bytes_per_launch"]
+                    r["algorithmic_bytes_per_launch"] = breakdown_all[n]["bytes"] / max(1, breakdown_all[n]["calls"])
+                    r["traffic_source"] = tr["source"]
+                rooflines[n] = r
         line = {"metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -727,7 +760,7 @@ def main():
                 "cuda_graphs": graphs_flag,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 4 * world, "last_loss": loss_host},
-                "roofline": roof, "kernel_breakdown": breakdown}
+                "roofline": roof, "rooflines": rooflines, "kernel_breakdown": breakdown}
         if eval_obj is not None:
             line["eval"] = eval_obj
         if world == 1 and not args.no_cpu_baseline:

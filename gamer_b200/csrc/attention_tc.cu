@@ -376,15 +376,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int g = h / (p.n_q / p.n_kv);
     const int kt_all = (p.L + S_KT - 1) / S_KT;
 
-    if (threadIdx.x == 0) {
-        prefetch_tmap(&tmQ);
-        prefetch_tmap(&tmK);
-        prefetch_tmap(&tmV);
-        prefetch_tmap(&tmO);
-        for (int i = 0; i < 14; ++i) mbar_init(&bars[i], (i == 10 || i == 11) ? 256 : 1);
-        fence_barrier_init();
-    }
     if (warp == 8) {
+        // the issuer warp sets the barriers up itself, so the Q tile (which does not depend on the key range) is already
+        // in flight while the TMEM allocation and the key-range scan below run
+        if (lane == 0) {
+            prefetch_tmap(&tmQ);
+            prefetch_tmap(&tmK);
+            prefetch_tmap(&tmV);
+            prefetch_tmap(&tmO);
+            for (int i = 0; i < 14; ++i) mbar_init(&bars[i], (i == 10 || i == 11) ? 256 : 1);
+            fence_barrier_init();
+            mbar_expect_tx(q_full, TILE_BYTES);
+            tma_load_3d(smem + S_OFF_Q, &tmQ, q_full, h * D, qt * BT, b);
+        }
+        __syncwarp();
         tmem_alloc<256>(tmem_slot);
         // Key-tile range of this CTA: leading tiles without a valid key (left padding) and trailing tiles that no query of
         // the tile can see are never loaded.  Lane t looks at 64-key tiles t and t + 32.
@@ -484,11 +489,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             __syncwarp();
         };
         if (nkt > 0) {
-            if (elect_one()) {
-                mbar_expect_tx(q_full, TILE_BYTES);
-                tma_load_3d(smem + S_OFF_Q, &tmQ, q_full, h * D, qt * BT, b);
-            }
-            __syncwarp();
             for (int n = 0; n < S_KST && n < nkt; ++n) load_k(n);
             for (int n = 0; n < S_VST && n < nkt; ++n) load_v(n);
             mbar_wait(q_full, 0);
@@ -653,13 +653,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (threadIdx.x == 0) {
             tma_store_3d(&tmO, smem + S_OFF_Q, h * D, qt * BT, b);
             bulk_commit();
-            bulk_wait0();
+            bulk_wait_read0();   // the CTA may retire once the store has read the staging tile
             trace_pt(tr, 1, tn, 26);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<256>(tmem_base);
+    if (warp == 8) {
+        // a CTA that never waited on q_full (empty key range) must not retire with the Q load still writing its smem
+        if (nkt == 0) mbar_wait(q_full, 0);
+        tmem_dealloc<256>(tmem_base);
+    }
 }
 
 // =================================================================================================================
