@@ -223,8 +223,8 @@ __device__ __forceinline__ float max32(const uint32_t* s) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // dropout keep words.  Word (bh, i, jw) covers keys [32 jw, 32 jw + 32) of query i; key 32 jw + 4 g + e <-> bit g + 8 e
-// (so that one shift brings the flags of four consecutive keys to the four byte sign positions).  Lane bit c of the eight
-// Philox words r0..r7 (two calls) forms the 8-bit number R_c; the key is dropped iff R_c < thresh.
+// (so that one shift brings the flags of four consecutive keys to the four byte sign positions).  Lane bit c of eight
+// random words r0..r7 (one Philox call, see keep_word) forms the 8-bit number R_c; the key is dropped iff R_c < thresh.
 // ---------------------------------------------------------------------------------------------------------------
 struct KeepGen {
     uint32_t k0, k1, site;
@@ -240,9 +240,15 @@ __device__ __forceinline__ KeepGen keep_gen(const DropParams& d) {
     return g;
 }
 __device__ __forceinline__ uint32_t keep_word(const KeepGen& g, uint32_t bh, uint32_t i, uint32_t jw) {
-    const uint4 a = philox4x32_7(2u * jw, i, bh, g.site, g.k0, g.k1);
-    const uint4 b = philox4x32_7(2u * jw + 1u, i, bh, g.site, g.k0, g.k1);
-    const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    // One Philox call per (query, 32-key block).  Its four words are the four HIGH bit planes of the 32 lane numbers R_c;
+    // the four LOW planes are the same words rotated by 5, 13, 21 and 29 bits, i.e. lane c's low bit k is the high bit k
+    // of lane c - rot_k: all eight bits of R_c still come from eight distinct (word, bit) cells of the generator's
+    // output, so every R_c is exactly uniform on 0..255 and the drop probability is exactly thresh / 256; what is given
+    // up is the independence between one lane's low bits and another lane's high bits, which a dropout mask never sees
+    // (the low planes decide only when the high nibble ties with the threshold's).  Halves the generator's cost.
+    const uint4 a = philox4x32_7(jw, i, bh, g.site, g.k0, g.k1);
+    const uint32_t r[8] = {__funnelshift_l(a.x, a.x, 5), __funnelshift_l(a.y, a.y, 13), __funnelshift_l(a.z, a.z, 21),
+                           __funnelshift_l(a.w, a.w, 29), a.x, a.y, a.z, a.w};
     uint32_t bo = 0u;   // borrow of R - thresh, least significant bit first: bo = (R < thresh) per lane
 #pragma unroll
     for (int k = 0; k < 8; ++k) bo = (~r[k] & g.tm[k]) | (~(r[k] ^ g.tm[k]) & bo);
@@ -1513,41 +1519,58 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // Padded per-row inputs of the backward: dsum_p[b,h,i] = keep_prob * sum_d dO*O and lse_p[b,h,i] = lse + log2(keep_prob)
 // (so that exp2(s - lse_p) = P / keep_prob); uniform rows keep dsum unscaled and lse = +inf; rows i >= L: 0 / +inf.
 // uni_bits[b] |= 1 << (i / 128) for uniform rows (head 0 decides: the mask is head-independent).
+constexpr int PREP_G = 4;   // (row, head) groups per 8-lane team: all eight 16-byte loads in flight before the first use
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ld_o, int B, int L,
                                      int Lp, int n_q, const float* __restrict__ lse, float keep_prob, float log2_keep,
                                      float* __restrict__ dsum_p, float* __restrict__ lse_p, unsigned* __restrict__ uni_bits) {
-    // grid = (groups of one sequence / 32, B); 8 threads per (padded row, head) group, 32-bit index math only
+    // grid = (teams of one sequence / 32, B); 8 threads per (padded row, head) group, PREP_G consecutive groups per team,
+    // 32-bit index math only
     const int b = blockIdx.y;
     const int sub = threadIdx.x & 7;
-    const int grp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);   // (row i, head h) of sequence b
-    const bool live = grp < Lp * n_q;
-    const int i = live ? grp / n_q : 0;
-    const int h = live ? grp - i * n_q : 0;
-    const bool real = live && i < L;
-    const long long row = real ? (long long)b * L + i : 0;
-    float a[8], d[8];
-    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8), a);
-    bf16x8_to_float(*reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8), d);
-    float s = 0.f;
+    const int team = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const int n_grp = Lp * n_q;
+    bf16x8 av[PREP_G], dv[PREP_G];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += a[k] * d[k];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (live && sub == 0) {
-        const long long pi = ((long long)b * n_q + h) * Lp + i;
-        float ls = INFINITY;
-        if (real) {
-            ls = lse[((long long)b * n_q + h) * L + i];
-            if (ls == INFINITY) {
-                if (h == 0) atomicOr(&uni_bits[b], 1u << (i / BT));
-            } else {
-                ls += log2_keep;
-                s *= keep_prob;
+    for (int j = 0; j < PREP_G; ++j) {
+        const int grp = team * PREP_G + j;
+        const bool live = grp < n_grp;
+        const int i = live ? grp / n_q : 0;
+        const int h = live ? grp - i * n_q : 0;
+        const long long row = (live && i < L) ? (long long)b * L + i : 0;
+        av[j] = *reinterpret_cast<const bf16x8*>(o + row * ld_o + h * D + sub * 8);
+        dv[j] = *reinterpret_cast<const bf16x8*>(d_o + row * ld_o + h * D + sub * 8);
+    }
+#pragma unroll
+    for (int j = 0; j < PREP_G; ++j) {
+        const int grp = team * PREP_G + j;
+        const bool live = grp < n_grp;
+        const int i = live ? grp / n_q : 0;
+        const int h = live ? grp - i * n_q : 0;
+        const bool real = live && i < L;
+        float a[8], d[8];
+        bf16x8_to_float(av[j], a);
+        bf16x8_to_float(dv[j], d);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += a[k] * d[k];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (live && sub == 0) {
+            const long long pi = ((long long)b * n_q + h) * Lp + i;
+            float ls = INFINITY;
+            if (real) {
+                ls = lse[((long long)b * n_q + h) * L + i];
+                if (ls == INFINITY) {
+                    if (h == 0) atomicOr(&uni_bits[b], 1u << (i / BT));
+                } else {
+                    ls += log2_keep;
+                    s *= keep_prob;
+                }
             }
+            dsum_p[pi] = real ? s : 0.f;
+            lse_p[pi] = ls;
         }
-        dsum_p[pi] = real ? s : 0.f;
-        lse_p[pi] = ls;
     }
 }
 
@@ -1753,7 +1776,7 @@ int attn_tc_bwd(const void* q, const void* k, const void* v, long long ld, int B
     GAMER_CHECK_CUDA(cudaMemsetAsync(uni, 0, (size_t)B * 4, stream));
     {
         const float keep_prob = 1.0f / dp.scale;
-        const dim3 grid((bl.ml.Lp * n_q * 8 + 255) / 256, B);
+        const dim3 grid(((bl.ml.Lp * n_q + PREP_G - 1) / PREP_G * 8 + 255) / 256, B);
         attn_bwd_prep_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o),
                                                        ld_o, B, L, bl.ml.Lp, n_q, lse, keep_prob, log2f(keep_prob), dsum,
                                                        lse_p, uni);

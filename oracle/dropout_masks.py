@@ -63,15 +63,18 @@ def hidden_keep(seed, offset, site, rows, cols, p):
 
 def attn_keep_words(seed, offset, site, B, n_q, L, p):
     """-> (uint32 [B*n_q, L, ceil(L/32)] keep words, scale): the words the forward kernel stores (attention_tc.cu:
-    keep_word).  Word (bh, i, jw) covers keys [32 jw, 32 jw + 32): two Philox calls give eight random words r0..r7; lane
-    bit c of r_k is bit k of an 8-bit number R_c, and the lane is dropped iff R_c < thresh."""
+    keep_word).  Word (bh, i, jw) covers keys [32 jw, 32 jw + 32): one Philox call gives the four high bit planes r4..r7,
+    the low planes r0..r3 are those words rotated left by 5, 13, 21, 29; lane bit c of r_k is bit k of an 8-bit number R_c,
+    and the lane is dropped iff R_c < thresh."""
     t, scale = _thresh(p, 8)
     k0, k1 = _key(seed, offset)
     nw = (L + 31) // 32
     bh = np.arange(B * n_q, dtype=np.uint64).reshape(B * n_q, 1, 1)
     i = np.arange(L, dtype=np.uint64).reshape(1, L, 1)
     jw = np.arange(nw, dtype=np.uint64).reshape(1, 1, nw)
-    r = philox4x32(2 * jw, i, bh, site, k0, k1) + philox4x32(2 * jw + 1, i, bh, site, k0, k1)
+    hi = philox4x32(jw, i, bh, site, k0, k1)                        # the four high bit planes
+    rotl = lambda x, n: ((x << np.uint32(n)) | (x >> np.uint32(32 - n))).astype(np.uint32)
+    r = tuple(rotl(hi[k].astype(np.uint32), 5 + 8 * k) for k in range(4)) + tuple(h.astype(np.uint32) for h in hi)
     lanes = np.zeros((B * n_q, L, nw, 32), dtype=np.uint32)       # R_c per lane
     bit = np.arange(32, dtype=np.uint32)
     for k in range(8):
