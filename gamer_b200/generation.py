@@ -55,6 +55,9 @@ def _resolve_constraint(prefix_allowed_tokens_fn, candidate_trie, vocab, pad, de
     # device copies are cached on the host objects: a captured decode graph holds their addresses
     cache = flat.__dict__.setdefault("_dev_cache", {})
     if device not in cache:
+        # the beam step indexes the logits with the trie's tokens: validate them once, on the host copy
+        if flat.child_tok.numel() and (int(flat.child_tok.max()) >= vocab or int(flat.child_tok.min()) < 0):
+            raise ValueError(f"candidate trie holds token ids outside the vocabulary [0, {vocab})")
         cache[device] = flat.to(device)
     flat_dev = cache[device]
     owner = prefix_allowed_tokens_fn if isinstance(prefix_allowed_tokens_fn, _PrefixFn) else flat
