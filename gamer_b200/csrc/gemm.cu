@@ -675,14 +675,9 @@ extern "C" int gamer_gemm_bf16_tn(const void* A, long long lda, int rows, const 
     if (int e = make_tmap_bf16(&tmA, A, rows, K, lda, BLOCK_M)) return e;
     // staged (TMA-store) epilogue whenever output rows are the A rows; fp32 outputs carry no residual in this code base
     const bool staged = row_map == nullptr && !(c_is_f32 && resid != nullptr);
-    static int wide_min_n = -1;   // GAMER_GEMM_WIDE_MIN_N: smallest N that takes 128 x 256 tiles (tuning / A-B switch)
-    if (wide_min_n < 0) {
-        const char* e = getenv("GAMER_GEMM_WIDE_MIN_N");
-        wide_min_n = (e != nullptr && atoi(e) > 0) ? atoi(e) : 512;
-    }
     // 128 x 256 tiles for the wide projections, and for the N = 256 dgrads with a long reduction and no residual tile
     // (measured per shape with tools/gemm_bench.py; the residual GEMMs of width 256 are faster with 128 x 128 tiles)
-    const bool wide = staged && !c_is_f32 && N % 256 == 0 && (N >= wide_min_n || (resid == nullptr && K >= 768));
+    const bool wide = staged && !c_is_f32 && N % 256 == 0 && (N >= 512 || (resid == nullptr && K >= 768));
     if (int e = make_tmap_bf16(&tmB, B, (long long)n_groups * N, K, ldb, wide ? 256 : 128)) return e;
     GemmParams p{rows, N, K, n_groups, seg_off, C, ldc, reinterpret_cast<const bf16*>(resid), ldr, row_map, alpha,
                  make_drop(drop, 16)};
