@@ -54,10 +54,16 @@ struct GemmCfg {
     static constexpr int OFF_C = STAGES * STAGE_BYTES;
     static constexpr int OFF_BAR = OFF_C + C_BUFS * C_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024 /*align*/;
+    // Epilogue warp sets.  With K = 256 a 128 x 256 tile is only 2 k clocks of MMA while four warps need ~3x that to move
+    // its 64 KB through TMEM -> registers -> shared memory -> TMA store: the epilogue, not the tensor pipe, paces the wide
+    // projections.  The 128 x 256 bf16 variant therefore runs TWO sets of four epilogue warps, one per 128-column half
+    // (each half already has its own staging buffer).
+    static constexpr int EPI_SETS = (STAGED && !OUT_F32 && BN == 256) ? 2 : 1;
+    static constexpr int THREADS = 64 + 128 * EPI_SETS;
 };
 
 template <bool OUT_F32, bool STAGED, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<OUT_F32, STAGED, BN>::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
     using S = GemmCfg<OUT_F32, STAGED, BN>;
@@ -91,7 +97,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);
+            mbar_init(&tempty_bar[s], 4 * S::EPI_SETS);
         }
         for (int s = 0; s < 3; ++s) {
             mbar_init(&c_free[s], 1);
@@ -210,6 +216,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int trow = quarter * 32 + lane;
+        const int eset = (warp - 2) >> 2;                 // epilogue warp set (0 unless EPI_SETS == 2)
+        const bool leader = (warp == 2 + 4 * eset) && lane == 0;
         const DropParams drop = drop_resolve(p.drop);
         int acc = 0;
         uint32_t acc_phase = 0, tcount = 0;
@@ -220,14 +228,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
             if constexpr (STAGED) {
               constexpr int NB = S::C_BUFS > 0 ? S::C_BUFS : 1;
+              // one set: it walks the halves; two sets: set e owns half e (and staging buffer e) of every tile
+              const int half_lo = S::EPI_SETS == 2 ? eset : 0, half_hi = S::EPI_SETS == 2 ? eset + 1 : HALVES;
 #pragma unroll 1
-              for (int half = 0; half < HALVES; ++half) {
+              for (int half = half_lo; half < half_hi; ++half) {
                 const uint32_t hc = tcount * HALVES + half;
                 const int cbuf = hc % NB;
                 const uint32_t use = hc / NB;
                 if (has_resid) mbar_wait(&r_full[cbuf], use & 1);
                 else mbar_wait(&c_free[cbuf], (use & 1) ^ 1);
-                if (half == 0) {
+                if (half == half_lo) {
                     mbar_wait(&tfull_bar[acc], acc_phase);
                     tc_fence_after();
                 }
@@ -235,10 +245,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sw = trow & 7;
                 const int col_half = n_blk * BN + half * 128;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + half * 128 + c * 32, r);
-                    tmem_ld_wait();
+                for (int c2 = 0; c2 < 4; c2 += 2) {
+                  // two 32-column chunks per TMEM round trip
+                  uint32_t rr[2][32];
+                  tmem_ld_32x32(taddr + half * 128 + c2 * 32, rr[0]);
+                  tmem_ld_32x32(taddr + half * 128 + c2 * 32 + 32, rr[1]);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int ci = 0; ci < 2; ++ci) {
+                    const int c = c2 + ci;
+                    const uint32_t* r = rr[ci];
                     if constexpr (OUT_F32) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
@@ -267,15 +283,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             sts128(addr, o.u[0], o.u[1], o.u[2], o.u[3]);
                         }
                     }
+                  }
                 }
-                if (half == HALVES - 1) {
+                if (half == half_hi - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
                 fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (warp == 2 && lane == 0) {
+                named_bar_sync(1 + eset, 128);
+                if (leader) {
                     constexpr int NBOX = OUT_F32 ? 4 : 2;
                     constexpr int BOX_COLS = OUT_F32 ? 32 : 64;
                     const uint8_t* sbuf = smem + S::OFF_C + cbuf * S::C_BYTES;
@@ -284,7 +301,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (col_half + bx * BOX_COLS < p.N)
                             tma_store_2d(&tmC, sbuf + bx * TILE16K, col_half + bx * BOX_COLS, row0);
                     bulk_commit();
-                    if (hc > 0) {  // every store but the one just issued has been read out: recycle its buffer
+                    if constexpr (S::EPI_SETS == 2) {
+                        // this set owns the buffer: hand it on (to the producer's residual load or to the set's next tile)
+                        // as soon as the store has read it out
+                        bulk_wait_read0();
+                        mbar_arrive(&c_free[cbuf]);
+                    } else if (hc > 0) {  // every store but the one just issued has been read out: recycle its buffer
                         bulk_wait_read1();
                         mbar_arrive(&c_free[(hc - 1) % NB]);
                     }
@@ -357,7 +379,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-        if (STAGED && warp == 2 && lane == 0) bulk_wait0();
+        if (STAGED && leader) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
@@ -653,7 +675,7 @@ int launch_gemm_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
         GAMER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     const int tiles = ceil_div(p.rows, BLOCK_M) * ceil_div(p.N, BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NUM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
+    kern<<<grid, S::THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, p);
     GAMER_LAUNCH_CHECK();
     return 0;
 }
