@@ -35,9 +35,9 @@ def parse():
                          "(train_MB_decoder: Qwen3Moe, 4 behaviour types, max_his_len 200); long_history = configs[4] "
                          "(Qwen3Multi max_his_len 500, batch sweep 256-4096)")
     ap.add_argument("--global-batch", type=int, default=1024)
-    ap.add_argument("--micro-batch", type=int, default=512,
-                    help="rows per forward+backward pass (gradient accumulation over the per-GPU batch); 512 rows keep "
-                         "~36 GB of activations and amortise the ~500 kernel launches of a pass")
+    ap.add_argument("--micro-batch", type=int, default=1024,
+                    help="rows per forward+backward pass (gradient accumulation over the per-GPU batch); 1024 rows keep "
+                         "~72 GB of activations of the 180 GB and run the step as one pass (2.5 %% faster than 2 x 512)")
     ap.add_argument("--max-his-len", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from the host (A/B switch)")
@@ -314,7 +314,7 @@ def eval_leg(args, dev, world, rank, barrier):
                            "traffic": None, "share_of_call": top["ms"] / total, "avg_launch_ms": top["ms"] / max(1, top["calls"]),
                            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("eval", {}).get(name)
             if tr and users == 256 and world == 1:
                 obj["roofline"]["traffic"] = tr["bytes_per_launch"]
                 obj["roofline"]["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
@@ -716,8 +716,9 @@ def main():
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None}
         try:   # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
-            if tr and mb == 512:                 # the captures were taken at the default micro-batch (512 rows)
+            # captures are keyed by the micro-batch rows they were taken at (512 and 1024)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(str(mb), {}).get(name)
+            if tr:
                 roof["traffic"] = tr["bytes_per_launch"]
                 roof["traffic_unit"] = "bytes/launch"
                 roof["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
@@ -748,7 +749,7 @@ def main():
         # capture at this micro-batch is committed (profiles/ncu_traffic.json)
         rooflines = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(str(mb), {})
         except Exception:
             traffic = {}
         for n in ("gamer_gemm_bf16_tn", "gamer_gemm_bf16_wgrad", "gamer_attn_fwd", "gamer_attn_bwd", "gamer_embed_route_fwd",
@@ -756,7 +757,7 @@ def main():
             if n in breakdown_all and breakdown_all[n]["ms"] > 0:
                 r = _roofline_of(n, breakdown_all[n], step_ms, peaks)
                 tr = traffic.get(n)
-                if tr and mb == 512:
+                if tr:
                     r["traffic"] = tr["bytes_per_launch"]
                     r["algorithmic_bytes_per_launch"] = breakdown_all[n]["bytes"] / max(1, breakdown_all[n]["calls"])
                     r["traffic_source"] = tr["source"]

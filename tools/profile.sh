@@ -7,14 +7,14 @@ TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --set full --clock-control none --import-source on -f"
-# every launch of one headline step (global batch 1024 = 2 passes of 512 rows) with its device time (cold-cache,
+# every launch of one headline step (global batch 1024 = one pass of 1024 rows) with its device time (cold-cache,
 # serialised: compare SHARES, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $OUT/launches_$TAG.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-eval --no-cuda-graphs > $OUT/launches_$TAG.stdout 2>&1
-# attention kernels at the bench's micro-batch (512 rows, L = 505, dropout 0.2): self (kind 0) and cross (kind 1)
+# attention kernels at the bench's micro-batch (1024 rows, L = 505, dropout 0.2): self (kind 0) and cross (kind 1)
 for K in 0 1; do
   timeout 300 $NCU -k regex:'attn_bwd_kernel|attn_fwd_kernel' -s 2 -c 2 -o $OUT/prof_${TAG}_attn_k$K \
-    python tools/attn_one.py --kind $K --p 0.2 --batch 512 --iters 2 --bench-levels > $OUT/prof_${TAG}_attn_k$K.stdout 2>&1
+    python tools/attn_one.py --kind $K --p 0.2 --batch 1024 --iters 2 --bench-levels > $OUT/prof_${TAG}_attn_k$K.stdout 2>&1
 done
 # decode kernels at the eval shape (256 users x 20 beams, 501-token prompts)
 timeout 300 $NCU -k regex:'attn_decode_kernel|beam_step_kernel' -s 26 -c 4 -o $OUT/prof_${TAG}_decode \
