@@ -309,27 +309,39 @@ __global__ void emb_reduce_kernel(const bf16* __restrict__ dx, int H, const int*
             const int c = c0 + lane;
             const bool col_ok = c < H / 8;
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int cc = col_ok ? c : 0;
             for (int i = 0; i < n; i += 8) {      // 8 rows (4 KB per warp) in flight
+                // every load is unconditional (past the end of the chunk it re-reads the chunk's last row, a cache hit, and
+                // the sum skips it): predicated loads made the compiler reuse destination registers, which serialised them
                 bf16x8 r[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int k = i + u;
+                    const int k = min(i + u, n - 1);
                     const int row = __shfl_sync(0xffffffffu, k < 32 ? idx0 : idx1, k & 31);
-                    r[u].u[0] = r[u].u[1] = r[u].u[2] = r[u].u[3] = 0u;
-                    if (k < n && col_ok) r[u] = *reinterpret_cast<const bf16x8*>(dx + (long long)row * H + c * 8);
+                    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(dx + (long long)row * H + cc * 8));
+                    r[u].u[0] = t.x; r[u].u[1] = t.y; r[u].u[2] = t.z; r[u].u[3] = t.w;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     float f[8];
                     bf16x8_to_float(r[u], f);
+                    const float keep = (i + u < n) ? 1.f : 0.f;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], keep, acc[k]);
                 }
             }
+            // behaviour tokens are a fifth of all rows, so thousands of chunks land on the same table row at the same
+            // time: two 16-byte vector reductions per lane instead of eight scalar ones (same-address serialisation in L2
+            // was what held this kernel at 30 % of HBM peak)
             float* out = dtable + (long long)v * H + c * 8;
             if (col_ok) {
+                if ((reinterpret_cast<unsigned long long>(out) & 15ull) == 0) {
+                    atomicAdd(reinterpret_cast<float4*>(out), make_float4(acc[0], acc[1], acc[2], acc[3]));
+                    atomicAdd(reinterpret_cast<float4*>(out) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) atomicAdd(out + k, acc[k]);
+                    for (int k = 0; k < 8; ++k) atomicAdd(out + k, acc[k]);
+                }
             }
         }
     }
