@@ -394,6 +394,8 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
             dp += ld_dout;
         }
     }
+    int act_next = HAS_EMB ? a.act_idx[mc0] : 0;
+    int p_next = a.pos_ids ? a.pos_ids[mc0] : 0;
     for (int it = 0; it < tr.iters; it += PF) {
 #pragma unroll
       for (int j = 0; j < PF; ++j, ++m) {
@@ -406,15 +408,18 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
             rp += ld_raw;
             dp += ld_dout;
         }
-        const long long mi = m <= mlast ? m : mlast;
-        int act = 0;
+        // the action index and RoPE position of a token are fetched one token ahead: the embedding row and the cos / sin
+        // rows they select are dependent loads, which would otherwise sit behind a second memory latency every token
+        const long long mn = m + 1 <= mlast ? m + 1 : mlast;
+        const int act = act_next;
         if (HAS_EMB) {
-            act = a.act_idx[mi];
+            act_next = a.act_idx[mn];
             const HeadRow e = load_head_row(emb + (long long)act * width + hc, sub);
 #pragma unroll
             for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
-        const int p = a.pos_ids ? a.pos_ids[mi] : pos + a.pos0;
+        const int p = a.pos_ids ? p_next : pos + a.pos0;
+        if (a.pos_ids) p_next = a.pos_ids[mn];
         const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
         const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
         const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
