@@ -482,6 +482,11 @@ def run_secondary(args):
                                    ("gamer_attn_fwd", "masked_attention_fwd"), ("gamer_attn_bwd", "masked_attention_bwd")):
                     if key in summ:
                         line.setdefault("rooflines", {})[label] = _roofline_of(key, summ[key], ms, peaks)
+                # ... and the two embedding kernels alone at one full-size launch (512 rows x 2505 tokens: inside the step
+                # they run on 64-row passes, where launch latency shows)
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import embed_bench
+                line["embedding_kernels"] = embed_bench.run(batch=512, his=mhl, iters=10, dev=f"cuda:{local}")
         del resident, host
         torch.cuda.empty_cache()
     if rank == 0:

@@ -32,13 +32,9 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--his", type=int, default=500)
-    ap.add_argument("--iters", type=int, default=20)
-    a = ap.parse_args()
-    dev = "cuda:0"
+def run(batch=512, his=500, iters=20, dev="cuda:0"):
+    """The K1 kernels alone at one launch of batch x 5 (his + 1) tokens; returns one dict per kernel."""
+    a = argparse.Namespace(batch=batch, his=his, iters=iters)
     L = 5 * (a.his + 1)
     V, H = syn.VOCAB, 256
     try:
@@ -67,11 +63,23 @@ def main():
     ms_b = timed(lambda: K.embed_bwd(dx, V, sort_buf, dtab), a.iters)
     bytes_b = M * (4 + 2 * H) + V * H * 4
     ms_s = timed(lambda: K.embed_sort(ids.view(-1), V, syn.PAD), a.iters)
+    out = []
     for name, ms, nbytes in (("gamer_embed_route_fwd", ms_f, bytes_f), ("gamer_embed_bwd", ms_b, bytes_b),
                              ("gamer_embed_sort_build (ids only: 8 B read + 4 B written per token)", ms_s, M * 12)):
         gbs = nbytes / (ms / 1e3) / 1e9
-        print(json.dumps({"kernel": name, "tokens": M, "batch": a.batch, "seq_len": L, "ms": ms, "algorithmic_bytes": nbytes,
-                          "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "peak_source": src}))
+        out.append({"kernel": name, "tokens": M, "batch": a.batch, "seq_len": L, "ms": ms, "algorithmic_bytes": nbytes,
+                    "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "peak_source": src})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--his", type=int, default=500)
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    for row in run(a.batch, a.his, a.iters):
+        print(json.dumps(row))
 
 
 if __name__ == "__main__":
