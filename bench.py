@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=1024,
                     help="rows per forward+backward pass (gradient accumulation over the per-GPU batch); 1024 rows keep "
                          "~72 GB of activations of the 180 GB and run the step as one pass (2.5 %% faster than 2 x 512)")
+    ap.add_argument("--workload-micro-batch", type=int, default=None,
+                    help="rows per pass of the mb_decoder / long_history workloads (defaults: 512 / 96)")
     ap.add_argument("--max-his-len", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel from the host (A/B switch)")
@@ -385,7 +387,7 @@ def run_secondary(args):
         cfg.num_behavior = 4
         cfg.behavior_maps = {str(t): i for i, t in enumerate(beh_tokens)}
         model = modeling.Qwen3MoeWithTemperature(cfg)
-        batches, mb_rows = [args.global_batch if args.global_batch != 1024 else 512], 256
+        batches, mb_rows = [args.global_batch if args.global_batch != 1024 else 512], 512
         make = lambda rows, seed: syn.make_mb_batch(cat, rows, max_his_len=mhl, behavior_tokens=beh_tokens, seed=seed)
         what = ("Qwen3Moe multi-behaviour decoder train (configs[3]: train_MB_decoder, 4 behaviour types, no sessions), "
                 f"max_his_len={mhl}")
@@ -393,10 +395,14 @@ def run_secondary(args):
         mhl = 500
         cfg = model_config(mhl)
         model = modeling.Qwen3MultiWithTemperature(cfg)
-        batches, mb_rows = [256, 512, 1024, 2048, 4096], 64
+        # 96 rows x 3 kv heads = 288 (sequence, kv head) groups = 2 full waves of the attention backward's 148 persistent
+        # CTAs (64 rows = 192 groups left a third of the second wave idle: 914 -> 1 050 samples/s)
+        batches, mb_rows = [256, 512, 1024, 2048, 4096], 96
         make = lambda rows, seed: syn.make_train_batch(cat, rows, max_his_len=mhl, seed=seed, full_length=True)
         what = f"Qwen3Multi smb_explicit_decoder train, long-history stress (configs[4]), max_his_len={mhl}"
     L = 5 * (mhl + 1)
+    if args.workload_micro_batch:
+        mb_rows = args.workload_micro_batch
     model.set_hyper(0.7)
     model = model.to(dev).train()
     if world > 1:
