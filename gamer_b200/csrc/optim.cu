@@ -57,7 +57,49 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
         dst[i] = __float2bfloat16(src[i]);
 }
 
+// Batched out-of-place transpose of bf16 matrices (the dgrad copies of every weight after an optimizer step): block =
+// one 32x32 tile of one matrix, found by binary search over the matrices' tile offsets.
+// desc[i] = {src, dst, rows, cols, ld_src, ld_dst} (int64 each): dst[c * ld_dst + r] = src[r * ld_src + c].
+__global__ void __launch_bounds__(256) transpose_batch_kernel(const long long* __restrict__ desc,
+                                                              const int* __restrict__ tile_start, int n_mats) {
+    __shared__ unsigned short tile[32][33];
+    int lo = 0, hi = n_mats;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const long long* d = desc + 6 * lo;
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(d[0]);
+    unsigned short* dst = reinterpret_cast<unsigned short*>(d[1]);
+    const int rows = (int)d[2], cols = (int)d[3];
+    const long long ld_src = d[4], ld_dst = d[5];
+    const int t = (int)blockIdx.x - tile_start[lo];
+    const int tiles_x = (cols + 31) >> 5;
+    const int r0 = (t / tiles_x) << 5, c0 = (t % tiles_x) << 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = src[(long long)r * ld_src + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) dst[(long long)c * ld_dst + r] = tile[tx][ty + 8 * i];
+    }
+}
+
 }  // namespace
+
+extern "C" int gamer_transpose_bf16_batch(const long long* desc, const int* tile_start, int n_mats, int total_tiles,
+                                          cudaStream_t stream) {
+    if (n_mats == 0 || total_tiles == 0) return 0;
+    GAMER_REQUIRE(n_mats > 0 && total_tiles > 0, "bad transpose batch (%d matrices, %d tiles)", n_mats, total_tiles);
+    transpose_batch_kernel<<<total_tiles, 256, 0, stream>>>(desc, tile_start, n_mats);
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int gamer_sumsq_accumulate(const float* g, long long n, float* out, cudaStream_t stream) {
     if (n == 0) return 0;

@@ -211,20 +211,41 @@ class FlatPack(Pack):
             if l in a.inject:
                 d["beh_emb"] = Wb[p + "beh_emb"]
             self.layers.append(d)
+        self._tr_desc = None
+        self._build_transpose_table()          # built here, not lazily: refresh() also runs under CUDA-graph capture
+
+    def _transposes(self):
+        """(src, dst) pairs of 2-D bf16 views with dst == src.t(): every dgrad copy of the pack, experts one by one."""
+        pairs = [(self.emb, self.emb_t[:, :self.emb.shape[0]])]
+        for d in self.layers:
+            pairs += [(d["w_qkv"], d["w_qkv_t"]), (d["w_o"], d["w_o_t"])]
+            if "c_w_qkvg" in d:
+                pairs += [(d["c_w_qkvg"], d["c_w_qkvg_t"]), (d["c_w_o"], d["c_w_o_t"])]
+            for w, wt in ((d["w_gu"], d["w_gu_t"]), (d["w_d"], d["w_d_t"])):
+                E_ = wt.shape[0] // w.shape[1]
+                src, dst = w.view(E_, -1, w.shape[1]), wt.view(E_, w.shape[1], -1)
+                pairs += [(src[e], dst[e]) for e in range(E_)]
+        return pairs
 
     def refresh(self):
         """Re-derive the transposed (dgrad) copies IN PLACE after the optimizer rewrote the flat bf16 buffer: every
-        operand keeps its address, so CUDA graphs captured over this pack stay valid."""
-        self.emb_t[:, :self.emb.shape[0]].copy_(self.emb.t())
-        for d in self.layers:
-            d["w_qkv_t"].copy_(d["w_qkv"].t())
-            d["w_o_t"].copy_(d["w_o"].t())
-            if "c_w_qkvg" in d:
-                d["c_w_qkvg_t"].copy_(d["c_w_qkvg"].t())
-                d["c_w_o_t"].copy_(d["c_w_o"].t())
-            E_ = d["w_gu_t"].shape[0] // d["w_gu"].shape[1]
-            d["w_gu_t"].view(E_, d["w_gu"].shape[1], -1).copy_(d["w_gu"].view(E_, -1, d["w_gu"].shape[1]).transpose(1, 2))
-            d["w_d_t"].view(E_, d["w_d"].shape[1], -1).copy_(d["w_d"].view(E_, -1, d["w_d"].shape[1]).transpose(1, 2))
+        operand keeps its address, so CUDA graphs captured over this pack stay valid.  One batched-transpose launch over a
+        descriptor table built once (the ~40 per-matrix `copy_` kernels it replaces were 0.26 ms of every step, 2 % of an
+        8-GPU step)."""
+        if getattr(self, "_tr_desc", None) is None:
+            self._build_transpose_table()
+        K.transpose_batch(self._tr_desc, self._tr_start, self._tr_n, self._tr_tiles)
+
+    def _build_transpose_table(self):
+        rows, starts = [], [0]
+        for src, dst in self._transposes():
+            assert src.dim() == 2 and dst.shape == (src.shape[1], src.shape[0]) and src.stride(1) == 1 and dst.stride(1) == 1
+            rows.append([src.data_ptr(), dst.data_ptr(), src.shape[0], src.shape[1], src.stride(0), dst.stride(0)])
+            starts.append(starts[-1] + ((src.shape[0] + 31) // 32) * ((src.shape[1] + 31) // 32))
+        dev = self.emb.device
+        self._tr_desc = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self._tr_start = torch.tensor(starts, dtype=torch.int32).to(dev)
+        self._tr_n, self._tr_tiles = len(rows), starts[-1]
 
 
 _ROPE_CACHE: dict = {}

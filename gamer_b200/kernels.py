@@ -287,3 +287,9 @@ def beam_step(logits, vocab, n_users, beams, run_score, node, flat, err):
          ptr(flat.child_start), ptr(flat.child_tok), ptr(flat.child_node), flat.max_children, ptr(new_score),
          ptr(new_parent), ptr(new_tok), ptr(new_node), ptr(err), _stream())
     return new_score, new_parent, new_tok, new_node
+
+
+def transpose_batch(desc, tile_start, n_mats, total_tiles):
+    """dst = src.t() for every (src, dst) bf16 matrix pair of the descriptor table, one launch."""
+    call("gamer_transpose_bf16_batch", ptr(desc), ptr(tile_start), int(n_mats), int(total_tiles), _stream())
+

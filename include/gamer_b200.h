@@ -170,6 +170,12 @@ int gamer_adamw_step(float* p, const float* g, float* m, float* v, const unsigne
                      long long n, const float* hp, float beta1, float beta2, float eps, float weight_decay,
                      const float* gnorm_sq, float max_grad_norm, float grad_scale, gamer_stream_t stream);
 int gamer_cast_f32_bf16(const float* src, void* dst, long long n, gamer_stream_t stream);
+/* The transposed (dgrad) copies of every weight, rewritten in ONE launch after an optimizer step (what autograd of
+ * nn.Linear gets for free from the same storage: SeqRec/models/generative/Qwen3Multi/model.py:38-49,66,147-149).
+ * desc (device): n_mats x {src, dst, rows, cols, ld_src, ld_dst} as int64, bf16 matrices, dst[c][r] = src[r][c];
+ * tile_start (device int32[n_mats + 1]): prefix sum of ceil(rows/32) * ceil(cols/32); total_tiles = tile_start[n_mats]. */
+int gamer_transpose_bf16_batch(const long long* desc, const int* tile_start, int n_mats, int total_tiles,
+                               gamer_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,11 @@ def test_native_step_matches_oracle_adamw():
     assert agree / total >= 0.98, agree / total
     # the bf16 operand copy written by the AdamW kernel is the rounded master copy
     assert torch.equal(tr.flat_bf16.float(), tr.flat_p.to(torch.bfloat16).float())
+    # the batched transpose left every dgrad copy equal to the transposed operand the AdamW kernel just wrote
+    pairs = tr.pack._transposes()
+    assert len(pairs) > 10
+    for src, dst in pairs:
+        assert torch.equal(dst, src.t())
     # a second step runs on the refreshed pack and lowers the loss on the same batch
     loss2 = tr.step(batch, micro_batch=6)
     assert loss2.item() < loss.item()
