@@ -7,8 +7,10 @@ as text, `DecoderOnlyCollator` / `DecoderOnlyTestCollator` run the HF tokenizer 
 added tokens with fixed ids, so the whole data set reduces to three flat integer arrays + user offsets
 (`PackedSessions`, ~7 bytes per interaction).  `collate_train` / `collate_eval` turn a set of users into the tensors the
 collators emit — `input_ids, attention_mask, labels, session_ids, extended_session_ids, actions` — with a handful of
-vectorised tensor ops on whatever device the store lives on (pinned host memory -> one small H2D copy -> padding and
-expansion to 5 tokens per item on the GPU).  PyTorch is used for indexing only; nothing here is on the arithmetic path.
+vectorised tensor ops when the store lives on the host, and with ONE kernel launch (`gamer_collate_sessions`,
+csrc/collate.cu) when it lives on the GPU: pinned host memory -> one small H2D copy -> padding and expansion to 5 tokens
+per item on the device.  The tensor-op version below is the specification the kernel is tested against, bit for bit
+(tests/test_collate_gpu.py).
 
 Semantics kept (checked against `gamer_b200.synthetic`, whose batches follow the collators):
   * history = the user's last `max_his_len` items (+ the target item when training: `max_his_len + 1` items);
@@ -103,10 +105,31 @@ def _expand(store, idx, valid, behavior_tokens, behavior_level, pad):
     return {k: v.reshape(B, n * TOKENS_PER_ITEM).contiguous() for k, v in out.items()}
 
 
+_LUT_CACHE: dict = {}
+
+
+def _device_collate(store, users, n_max, width, left_pad, behavior_tokens, behavior_level, pad, target_behavior, labels):
+    """The whole batch in one launch (store on the GPU).  `width=None` costs one host sync for the longest kept history."""
+    from . import kernels as K
+    dev = store.offsets.device
+    if width is None:
+        n = torch.clamp(store.offsets[users + 1] - store.offsets[users], max=n_max)
+        width = int(n.max())
+    key = (tuple(int(t) for t in behavior_tokens), tuple(int(t) for t in behavior_level), str(dev))
+    lut = _LUT_CACHE.get(key)
+    if lut is None:
+        lut = (torch.tensor(key[0], dtype=torch.int64, device=dev), torch.tensor(key[1], dtype=torch.int64, device=dev))
+        if not torch.cuda.is_current_stream_capturing():
+            _LUT_CACHE[key] = lut
+    return K.collate_sessions(store, users, n_max, int(width), left_pad, lut[0], lut[1], pad, target_behavior, labels)
+
+
 def collate_train(store: PackedSessions, users, max_his_len: int, behavior_tokens, behavior_level, pad: int = 4,
                   width: int | None = None) -> dict:
     """DecoderOnlyCollator (train split, only_train_response=False): the last max_his_len + 1 items, right-padded."""
     users = torch.as_tensor(users, dtype=torch.int64, device=store.offsets.device)
+    if store.offsets.is_cuda:
+        return _device_collate(store, users, max_his_len + 1, width, False, behavior_tokens, behavior_level, pad, -1, True)
     idx, valid = _window(store, users, max_his_len + 1, left_pad=False, width=width)
     out = _expand(store, idx, valid, behavior_tokens, behavior_level, pad)
     labels = out["input_ids"].clone()
@@ -122,6 +145,9 @@ def collate_eval(store: PackedSessions, users, max_his_len: int, target_behavior
     """DecoderOnlyTestCollator + the target-behaviour append of test_SMB_decoder.py:105-117: the last max_his_len items,
     LEFT-padded, then one more column holding the target behaviour token (session max+1, extended max+1, its level)."""
     users = torch.as_tensor(users, dtype=torch.int64, device=store.offsets.device)
+    if store.offsets.is_cuda:
+        return _device_collate(store, users, max_his_len, width, True, behavior_tokens, behavior_level, pad,
+                               int(target_behavior), False)
     idx, valid = _window(store, users, max_his_len, left_pad=True, width=width)
     out = _expand(store, idx, valid, behavior_tokens, behavior_level, pad)
     B = users.numel()

@@ -293,3 +293,21 @@ def transpose_batch(desc, tile_start, n_mats, total_tiles):
     """dst = src.t() for every (src, dst) bf16 matrix pair of the descriptor table, one launch."""
     call("gamer_transpose_bf16_batch", ptr(desc), ptr(tile_start), int(n_mats), int(total_tiles), _stream())
 
+
+def collate_sessions(store, users, n_max, width, left_pad, beh_tokens, beh_level, pad, target_behavior, with_labels):
+    """gamer_collate_sessions: the collators' batch tensors from the packed store (all on the device), one launch."""
+    B = users.numel()
+    L = 5 * width + (1 if target_behavior >= 0 else 0)
+    dev = users.device
+    names = ["input_ids", "attention_mask", "session_ids", "extended_session_ids", "actions"] + (["labels"] if with_labels else [])
+    buf = torch.empty(len(names), B, L, dtype=torch.int64, device=dev)
+    out = {n: buf[i] for i, n in enumerate(names)}
+    toks = store.item_tokens
+    assert toks.dtype == torch.int32 and toks.is_contiguous() and store.behavior.dtype == torch.int16
+    assert store.session.dtype == torch.int32 and store.offsets.dtype == torch.int64 and users.dtype == torch.int64
+    call("gamer_collate_sessions", ptr(toks), ptr(store.behavior), ptr(store.session), ptr(store.offsets), ptr(users), B,
+         int(n_max), int(width), 1 if left_pad else 0, ptr(beh_tokens), ptr(beh_level), beh_tokens.numel(), int(pad),
+         int(target_behavior), ptr(out["input_ids"]), ptr(out["attention_mask"]), ptr(out.get("labels")),
+         ptr(out["session_ids"]), ptr(out["extended_session_ids"]), ptr(out["actions"]), _stream())
+    return out
+

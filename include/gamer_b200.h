@@ -162,6 +162,22 @@ int gamer_beam_step(const float* logits, long long ld, int vocab, int n_users, i
                     int max_children, float* new_score, int* new_parent, int* new_tok, int* new_node, int* err,
                     gamer_stream_t stream);
 
+/* ---- input pipeline ---------------------------------------------------------------------
+ * One launch builds the collators' batch tensors from the pre-tokenised interaction store: replaces
+ * DecoderOnlyCollator / DecoderOnlyTestCollator (SeqRec/datasets/collator.py:47-107,149-207), the per-sample
+ * session / extended-session / action arrays (SeqRec/datasets/SMB_dataset.py:194-234) and the target-behaviour column
+ * of SeqRec/tasks/test_SMB_decoder.py:105-117.  Store: item_tokens int32 [T,4], behavior int16 [T], session int32 [T],
+ * offsets int64 [N+1] (user u owns rows offsets[u]..offsets[u+1]-1, oldest first).  Row r = the last <= n_max items of
+ * users[r], 5 tokens per item, `width` items per row, right-padded (left_pad = 0, training) or left-padded (1,
+ * evaluation); target_behavior >= 0 appends one column (that behaviour's token, session max+1, extended max+1, its
+ * level).  Outputs int64 [n_users, 5*width (+1)]; labels may be NULL. */
+int gamer_collate_sessions(const int* item_tokens, const short* behavior, const int* session, const long long* offsets,
+                           const long long* users, int n_users, int n_max, int width, int left_pad,
+                           const long long* beh_tokens, const long long* beh_level, int n_beh, long long pad,
+                           int target_behavior, long long* input_ids, long long* attention_mask, long long* labels,
+                           long long* session_ids, long long* extended_session_ids, long long* actions,
+                           gamer_stream_t stream);
+
 /* ---- optimizer over the flat fused parameter buffer ------------------------------------
  * AdamW as HF Trainer configures it (SeqRec/tasks/train_SMB_decoder.py:396-428: adamw_torch, weight decay on non-norm
  * weights, clip_grad_norm_(max_grad_norm)).  hp (device floats): lr, 1-beta1^t, 1-beta2^t. */
