@@ -22,6 +22,7 @@ struct RouteArgs {
     int pad, eos, vocab;
     const int* beh_lut;    // [vocab] mapped behaviour index (+1), raw id when unmapped (router.py:122-123)
     int n_beh;             // clamp for the embedding lookups
+    int* err;              // nullable: bit 0 is set when a token id lies outside [0, vocab)
 };
 
 __device__ __forceinline__ void route_token(const RouteArgs& a, int b, int s, long long id, int& pos_i, int& beh_i,
@@ -60,6 +61,7 @@ embed_route_kernel(RouteArgs a, const bf16* __restrict__ table, int H, bf16* __r
         if (lane < TOK && m0 + lane < M) {
             const long long m = m0 + lane;
             id = a.ids[m];
+            if ((id < 0 || id >= a.vocab) && a.err != nullptr) atomicOr(a.err, 1);   // nn.Embedding raises here
             int p, be, ac;
             route_token(a, (int)(m / a.S), (int)(m % a.S), id, p, be, ac);
             pos_idx[m] = p;
@@ -352,13 +354,13 @@ __global__ void emb_reduce_kernel(const bf16* __restrict__ dx, int H, const int*
 extern "C" int gamer_embed_route_fwd(const long long* ids, const long long* ctx, long long ctx_ld, int B, int S, int pos0,
                                      int tokens_per_item, int pad, int eos, int vocab, const int* beh_lut, int n_beh,
                                      const void* table_bf16, int H, void* x_bf16, int* pos_idx, int* beh_idx,
-                                     int* act_idx, cudaStream_t stream) {
+                                     int* act_idx, int* err, cudaStream_t stream) {
     GAMER_REQUIRE(H % 8 == 0, "hidden size must be a multiple of 8");
     GAMER_REQUIRE(tokens_per_item >= 1, "tokens_per_item must be >= 1");
     const long long M = (long long)B * S;
     if (M == 0) return 0;
     RouteArgs a{ids, ctx ? ctx : ids, ctx ? ctx_ld : (long long)S, B, S, pos0, tokens_per_item, pad, eos, vocab,
-                beh_lut, n_beh};
+                beh_lut, n_beh, err};
     const int threads = 256, wpb = threads / 32;
     const long long groups = (M + TOK - 1) / TOK;
     const int grid = (int)((groups + wpb - 1) / wpb < 148 * 8 ? (groups + wpb - 1) / wpb : 148 * 8);

@@ -193,6 +193,7 @@ struct HeadArgs {
     int n_q, n_kv;
     const int* pos_ids;    // [M] RoPE positions or nullptr
     int pos0;              // added to m % L when pos_ids == nullptr (decode steps)
+    int n_pos;             // rows of the cos / sin tables: positions are clamped to [0, n_pos)
     const float* cos_tab;  // [n_pos, 32]
     const float* sin_tab;
     const float* qn_w;     // [64]
@@ -306,7 +307,7 @@ qk_norm_rope_fwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
 #pragma unroll
             for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
-        const int p = a.pos_ids ? a.pos_ids[mi] : pos + a.pos0;
+        const int p = min(max(a.pos_ids ? a.pos_ids[mi] : pos + a.pos0, 0), a.n_pos - 1);
         const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
         const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
         const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -418,7 +419,7 @@ qk_norm_rope_bwd_kernel(HeadArgs a, const bf16* __restrict__ raw, long long ld_r
 #pragma unroll
             for (int i = 0; i < 8; ++i) u.f[i] += e.f[i];
         }
-        const int p = a.pos_ids ? p_next : pos + a.pos0;
+        const int p = min(max(a.pos_ids ? p_next : pos + a.pos0, 0), a.n_pos - 1);
         if (a.pos_ids) p_next = a.pos_ids[mn];
         const float4 c4 = *reinterpret_cast<const float4*>(a.cos_tab + (long long)p * 32 + 4 * sub);
         const float4 s4 = *reinterpret_cast<const float4*>(a.sin_tab + (long long)p * 32 + 4 * sub);
@@ -532,11 +533,11 @@ extern "C" int gamer_rmsnorm_bwd(const void* x, const float* w, const float* rst
     return 0;
 }
 
-static HeadArgs make_head_args(long long M, int L, int n_q, int n_kv, const int* pos_ids, int pos0,
+static HeadArgs make_head_args(long long M, int L, int n_q, int n_kv, const int* pos_ids, int pos0, int n_pos,
                                const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
                                const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx, float eps) {
     HeadArgs a;
-    a.M = M; a.L = L; a.n_q = n_q; a.n_kv = n_kv; a.pos_ids = pos_ids; a.pos0 = pos0;
+    a.M = M; a.L = L; a.n_q = n_q; a.n_kv = n_kv; a.pos_ids = pos_ids; a.pos0 = pos0; a.n_pos = n_pos;
     a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.qn_w = qn_w; a.kn_w = kn_w;
     a.q_emb = reinterpret_cast<const bf16*>(q_emb); a.k_emb = reinterpret_cast<const bf16*>(k_emb);
     a.v_emb = reinterpret_cast<const bf16*>(v_emb); a.act_idx = act_idx; a.eps = eps;
@@ -544,13 +545,14 @@ static HeadArgs make_head_args(long long M, int L, int n_q, int n_kv, const int*
 }
 
 extern "C" int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* out, long long ld_out, long long M, int L,
-                                      int n_q, int n_kv, int head_dim, const int* pos_ids, int pos0,
+                                      int n_q, int n_kv, int head_dim, const int* pos_ids, int pos0, int n_pos,
                                       const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
                                       const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx,
                                       float eps, cudaStream_t stream) {
     GAMER_REQUIRE(head_dim == HD, "head kernels are specialised for head_dim 64 (got %d)", head_dim);
+    GAMER_REQUIRE(n_pos > 0, "the RoPE tables need at least one row (n_pos = %d)", n_pos);
     if (M == 0) return 0;
-    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
+    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, n_pos, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
                                 act_idx, eps);
     const int n_heads = n_q + 2 * n_kv;
     GAMER_REQUIRE(n_heads <= 48, "too many heads for the (8, heads, Z) block layout");
@@ -570,14 +572,15 @@ extern "C" int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* o
 
 extern "C" int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const void* dout, long long ld_dout, void* draw,
                                       long long ld_draw, long long M, int L, int n_q, int n_kv, int head_dim,
-                                      const int* pos_ids, int pos0, const float* cos_tab, const float* sin_tab,
+                                      const int* pos_ids, int pos0, int n_pos, const float* cos_tab, const float* sin_tab,
                                       const float* qn_w, const float* kn_w, const void* q_emb, const void* k_emb,
                                       const void* v_emb, const int* act_idx, int emb_rows, float eps, float* d_qn_w,
                                       float* d_kn_w, float* d_q_emb, float* d_k_emb, float* d_v_emb,
                                       cudaStream_t stream) {
     GAMER_REQUIRE(head_dim == HD, "head kernels are specialised for head_dim 64 (got %d)", head_dim);
+    GAMER_REQUIRE(n_pos > 0, "the RoPE tables need at least one row (n_pos = %d)", n_pos);
     if (M == 0) return 0;
-    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
+    HeadArgs a = make_head_args(M, L, n_q, n_kv, pos_ids, pos0, n_pos, cos_tab, sin_tab, qn_w, kn_w, q_emb, k_emb, v_emb,
                                 act_idx, eps);
     const bool has_emb = q_emb != nullptr;
     GAMER_REQUIRE(!has_emb || (d_q_emb && d_k_emb && d_v_emb), "behaviour-embedding grads missing");

@@ -282,6 +282,7 @@ def constrained_beam_search(model, input_ids, attention_mask, session_ids, exten
                 cache[key] = "seen"
             gen, run, err = fn(**inputs)
     _raise_on(int(err.item()))                                               # single host sync of the whole decode
+    K.check_token_ids(input_ids.device)                                      # (already synchronised: a second word read)
     seqs = torch.cat([input_ids.view(B, 1, L0).expand(B, beams, L0), gen], dim=2)
     scores = run / float(S)                                                  # length_penalty = 1: sum / generated length
     nret = num_return_sequences

@@ -37,6 +37,34 @@ def _req(t: torch.Tensor, dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------ K1
+_ID_ERR: dict = {}
+
+
+def _dev_key(device):
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def id_error_word(device):
+    """Per-device int32 word the gather kernel flags out-of-range token ids in (persistent: captured graphs hold it)."""
+    key = _dev_key(device)
+    w = _ID_ERR.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=device)
+        if torch.cuda.is_current_stream_capturing():
+            return w
+        _ID_ERR[key] = w
+    return w
+
+
+def check_token_ids(device):
+    """Raise what nn.Embedding raises if any token id since the last check was outside the vocabulary (one host sync)."""
+    w = _ID_ERR.get(_dev_key(device))
+    if w is not None and int(w.item()) != 0:
+        w.zero_()
+        raise IndexError("index out of range in self: a token id passed to the model is outside [0, vocab_size)")
+
+
 def embed_route(ids, table_bf16, beh_lut, n_beh, tokens_per_item, pad, eos, ctx=None, pos0=0, want_x=True):
     """ids int64 [B,S] -> (x bf16 [B*S,H] | None, pos_idx, beh_idx, act_idx int32 [B*S])."""
     _req(ids, torch.int64)
@@ -51,8 +79,8 @@ def embed_route(ids, table_bf16, beh_lut, n_beh, tokens_per_item, pad, eos, ctx=
     if ctx is not None:
         ctx = ctx.contiguous()
     call("gamer_embed_route_fwd", ptr(ids), ptr(ctx), 0 if ctx is None else ctx.shape[1], B, S, pos0, tokens_per_item,
-         pad, eos, V, ptr(beh_lut), n_beh, ptr(table_bf16), H, ptr(x), ptr(pos), ptr(beh), ptr(act), _stream(),
-         work=(0, B * S * (8 + 2 * H + 12)))        # id + bf16 row + 3 int32 indices per token (§8d)
+         pad, eos, V, ptr(beh_lut), n_beh, ptr(table_bf16), H, ptr(x), ptr(pos), ptr(beh), ptr(act),
+         ptr(id_error_word(dev)), _stream(), work=(0, B * S * (8 + 2 * H + 12)))        # id + bf16 row + 3 int32 indices per token (§8d)
     return x, pos, beh, act
 
 
@@ -113,8 +141,8 @@ def qk_norm_rope_fwd(raw, L, n_q, n_kv, hd, cos_tab, sin_tab, qn_w, kn_w, eps, p
     if out is None:
         out = torch.empty(M, width, dtype=BF16, device=raw.device)
     call("gamer_qk_norm_rope_fwd", ptr(raw), raw.stride(0), ptr(out), out.stride(0), M, L, n_q, n_kv, hd, ptr(pos_ids),
-         pos0, ptr(cos_tab), ptr(sin_tab), ptr(qn_w), ptr(kn_w), ptr(q_emb), ptr(k_emb), ptr(v_emb), ptr(act_idx), eps,
-         _stream())
+         pos0, cos_tab.shape[0], ptr(cos_tab), ptr(sin_tab), ptr(qn_w), ptr(kn_w), ptr(q_emb), ptr(k_emb), ptr(v_emb),
+         ptr(act_idx), eps, _stream())
     return out
 
 
@@ -123,8 +151,8 @@ def qk_norm_rope_bwd(raw, dout, draw, L, n_q, n_kv, hd, cos_tab, sin_tab, qn_w, 
                      d_v_emb=None):
     M = raw.shape[0]
     call("gamer_qk_norm_rope_bwd", ptr(raw), raw.stride(0), ptr(dout), dout.stride(0), ptr(draw), draw.stride(0), M, L,
-         n_q, n_kv, hd, ptr(pos_ids), pos0, ptr(cos_tab), ptr(sin_tab), ptr(qn_w), ptr(kn_w), ptr(q_emb), ptr(k_emb),
-         ptr(v_emb), ptr(act_idx), emb_rows, eps, ptr(d_qn_w), ptr(d_kn_w), ptr(d_q_emb), ptr(d_k_emb), ptr(d_v_emb),
+         n_q, n_kv, hd, ptr(pos_ids), pos0, cos_tab.shape[0], ptr(cos_tab), ptr(sin_tab), ptr(qn_w), ptr(kn_w), ptr(q_emb),
+         ptr(k_emb), ptr(v_emb), ptr(act_idx), emb_rows, eps, ptr(d_qn_w), ptr(d_kn_w), ptr(d_q_emb), ptr(d_k_emb), ptr(d_v_emb),
          _stream())
     return draw
 

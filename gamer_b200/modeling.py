@@ -173,6 +173,13 @@ class _GamerCausalLM(PreTrainedModel):
         sd.setdefault("lm_head.weight", self.model.embed_tokens.weight)
         return sd
 
+    def check_token_ids(self):
+        """nn.Embedding raises IndexError on a token id outside the vocabulary; the gather kernel cannot raise, it flags
+        the id in a device word.  This reads the word (one host sync) and raises: call it wherever the host synchronises
+        anyway (logging steps, end of an epoch); `generate` does so itself."""
+        from . import kernels as K
+        K.check_token_ids(self.device)
+
     def set_dropout_seed(self, seed: int):
         """Fix the Philox seed of the training-mode dropout masks (default: torch.initial_seed() mixed with the rank)."""
         self._drop_seed = int(seed)

@@ -190,6 +190,7 @@ def train_SMB_decoder(seed, backbone, base_model, output_dir, data_path, tasks, 
             seen += b["input_ids"].shape[0]
             if step % logging_step == 0:
                 _info(f"epoch {epoch} step {step}/{total_steps} loss {float(loss):.4f} lr {trainer.current_lr():.2e}")
+                model.check_token_ids()                      # the host is synchronised here anyway
         torch.cuda.synchronize()
         dt = time.time() - t0
         vl = torch.tensor([_valid_loss(model, valid, rank, world, per_device_batch_size, max_his_len, data)], device=dev)

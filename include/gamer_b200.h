@@ -52,11 +52,13 @@ typedef struct {
 /* ---- K1: embedding gather + router indices ------------------------------------------------------------------
  * replaces embed_tokens(input_ids) (Qwen3Multi/model.py:779) and Qwen3MultiDecoderRouter.forward
  * (Qwen3Multi/router.py:74-201; Qwen3Moe/router.py:74-154).  ids/ctx are int64 as the reference passes them.
- * Token s of row b sits at absolute position pos0+s; ctx (may be NULL = ids) is the whole sequence so far. */
+ * Token s of row b sits at absolute position pos0+s; ctx (may be NULL = ids) is the whole sequence so far.
+ * A token id outside [0, vocab) gathers the pad row and sets bit 0 of *err (device int32, may be NULL): nn.Embedding
+ * raises IndexError there, the caller reads the word when it next synchronises. */
 int gamer_embed_route_fwd(const long long* ids, const long long* ctx, long long ctx_ld, int B, int S, int pos0,
                           int tokens_per_item, int pad, int eos, int vocab, const int* beh_lut, int n_beh,
                           const void* table_bf16, int H, void* x_bf16, int* pos_idx, int* beh_idx, int* act_idx,
-                          gamer_stream_t stream);
+                          int* err, gamer_stream_t stream);
 /* expert routing permutation for MyQwen3SparseMLP (Qwen3Moe/FFN.py:53-72): expert = position index. */
 long long gamer_route_perm_workspace_bytes(int B);
 int gamer_route_perm_build(const int* pos_idx, int B, int S, int n_experts, void* workspace, int* perm, int* rows,
@@ -69,7 +71,9 @@ int gamer_embed_bwd(const void* dx_bf16, long long M, int H, int vocab, const vo
 
 /* ---- K2/K3: RMSNorm, head norm + behaviour embedding + RoPE ---------------------------------------------------
  * Qwen3RMSNorm (Qwen3Multi/model.py:165-176,205,222,239,284,869); q/k norm, behaviour embeddings and
- * apply_rotary_pos_emb (Qwen3Multi/model.py:88-101); FFN behaviour-embedding concat (Qwen3Moe/FFN.py:60-62). */
+ * apply_rotary_pos_emb (Qwen3Multi/model.py:88-101); FFN behaviour-embedding concat (Qwen3Moe/FFN.py:60-62).
+ * cos_tab / sin_tab: fp32 [n_pos, head_dim/2]; a position (pos_ids[m], or m % L + pos0) outside [0, n_pos) is clamped
+ * to the nearest table row instead of read out of bounds — size the tables for the largest position the caller uses. */
 int gamer_rmsnorm_fwd(const void* x, const float* w, float eps, long long M, int H, void* out, long long ld_out,
                       const int* row_map, const void* cat_table, const int* cat_idx, int cat_dim, float* rstd,
                       gamer_stream_t stream);
@@ -77,13 +81,13 @@ int gamer_rmsnorm_bwd(const void* x, const float* w, const float* rstd, float ep
                       long long ld_dh, const int* row_map, const void* dres, void* dx, float* dw, const int* cat_idx,
                       int cat_dim, int cat_rows, float* dcat, gamer_stream_t stream);
 int gamer_qk_norm_rope_fwd(const void* raw, long long ld_raw, void* out, long long ld_out, long long M, int L, int n_q,
-                           int n_kv, int head_dim, const int* pos_ids, int pos0, const float* cos_tab,
+                           int n_kv, int head_dim, const int* pos_ids, int pos0, int n_pos, const float* cos_tab,
                            const float* sin_tab, const float* qn_w, const float* kn_w, const void* q_emb,
                            const void* k_emb, const void* v_emb, const int* act_idx, float eps, gamer_stream_t stream);
 int gamer_qk_norm_rope_bwd(const void* raw, long long ld_raw, const void* dout, long long ld_dout, void* draw,
                            long long ld_draw, long long M, int L, int n_q, int n_kv, int head_dim, const int* pos_ids,
-                           int pos0, const float* cos_tab, const float* sin_tab, const float* qn_w, const float* kn_w,
-                           const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx, int emb_rows,
+                           int pos0, int n_pos, const float* cos_tab, const float* sin_tab, const float* qn_w,
+                           const float* kn_w, const void* q_emb, const void* k_emb, const void* v_emb, const int* act_idx, int emb_rows,
                            float eps, float* d_qn_w, float* d_kn_w, float* d_q_emb, float* d_k_emb, float* d_v_emb,
                            gamer_stream_t stream);
 

@@ -194,6 +194,27 @@ def test_embed_route_and_perm(left_pad):
     assert torch.equal(rows[perm], torch.arange(B * L))
 
 
+def test_embed_route_flags_out_of_vocabulary_ids():
+    """nn.Embedding raises IndexError on an id outside the table; the kernel gathers the pad row and flags it."""
+    k = _k()
+    spec = _spec()
+    V = spec.vocab_size
+    table = bf(torch.randn(V, 256)).to(DEV)
+    lut = _beh_lut(spec, V)
+    good = torch.randint(14, V, (2, 10), device=DEV)
+    k.check_token_ids(DEV)                                   # clears anything an earlier test left behind
+    k.embed_route(good, table, lut, spec.n_behavior, 5, spec.pad, spec.eos)
+    k.check_token_ids(DEV)                                   # nothing flagged
+    for bad_id in (V, V + 77, -1):
+        bad = good.clone()
+        bad[1, 3] = bad_id
+        x, *_ = k.embed_route(bad, table, lut, spec.n_behavior, 5, spec.pad, spec.eos)
+        assert torch.equal(x[13], table[spec.pad])
+        with pytest.raises(IndexError):
+            k.check_token_ids(DEV)
+        k.check_token_ids(DEV)                               # the word was reset by the failed check
+
+
 def test_embed_decode_step_route():
     from oracle import oracle_model as om
     k = _k()
@@ -319,6 +340,25 @@ def test_qk_norm_rope_fwd_bwd(cross):
     if cross:
         for mine, r in zip((dqe, dke, dve), embs):
             assert rel_err(mine, r.grad) < 2e-3
+
+
+def test_qk_norm_rope_positions_are_clamped_to_the_table():
+    """A position outside [0, n_pos) reads the nearest table row (never out of bounds): the result equals the one for the
+    clamped positions."""
+    from oracle import oracle_model as om
+    k = _k()
+    torch.manual_seed(3)
+    spec = _spec()
+    M, nq, nkv, hd, eps, n_pos = 64, 6, 3, 64, 1e-6, 50
+    raw = bf(torch.randn(M, 768, device=DEV))
+    qn = 1 + 0.1 * torch.randn(hd, device=DEV)
+    kn = 1 + 0.1 * torch.randn(hd, device=DEV)
+    cos, sin = om.rope_cos_sin(spec, torch.arange(n_pos).unsqueeze(0))
+    cos_t, sin_t = cos[0, :, :32].contiguous().to(DEV), sin[0, :, :32].contiguous().to(DEV)
+    wild = torch.randint(-40, 4000, (M,), dtype=torch.int32, device=DEV)
+    a = k.qk_norm_rope_fwd(raw, 1, nq, nkv, hd, cos_t, sin_t, qn, kn, eps, pos_ids=wild)
+    b = k.qk_norm_rope_fwd(raw, 1, nq, nkv, hd, cos_t, sin_t, qn, kn, eps, pos_ids=wild.clamp(0, n_pos - 1))
+    assert torch.equal(a, b)
 
 
 # ------------------------------------------------------------------------------------------------ attention
