@@ -251,6 +251,18 @@ inline int grid_for(long long total, int threads) {
     return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
 }
 
+// dst[r, 0..W) = 0 for every row r with rows[r] < 0 (the padding rows of the expert-permuted token space): a warp
+// per row, 16 bytes per lane; mapped rows are only looked at.
+__global__ void zero_unmapped_rows_kernel(bf16* __restrict__ dst, long long ld, const int* __restrict__ rows,
+                                          long long n_rows, int W) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long r = w0; r < n_rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+        if (rows[r] >= 0) continue;
+        for (int c = lane * 8; c < W; c += 256) *reinterpret_cast<uint4*>(dst + r * ld + c) = make_uint4(0, 0, 0, 0);
+    }
+}
+
 }  // namespace
 
 extern "C" int gamer_swiglu_fwd(const void* gu, long long ld_gu, void* act, long long ld_act, long long R, int I,
@@ -307,6 +319,17 @@ extern "C" int gamer_gather_rows(const void* src, long long ld_src, const int* r
     gather_rows_kernel<<<grid_for(n_rows_max * (W / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(src), ld_src, rows, n_rows_dev, n_rows_max, reinterpret_cast<bf16*>(dst), ld_dst, W,
         make_drop(drop, 16));
+    GAMER_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gamer_zero_unmapped_rows(void* dst, long long ld_dst, const int* rows, long long n_rows, int W,
+                                        cudaStream_t stream) {
+    GAMER_REQUIRE(W % 8 == 0 && ld_dst % 8 == 0, "width and row stride must be multiples of 8");
+    if (n_rows == 0) return 0;
+    const long long blocks = (n_rows + 7) / 8;
+    zero_unmapped_rows_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(
+        reinterpret_cast<bf16*>(dst), ld_dst, rows, n_rows, W);
     GAMER_LAUNCH_CHECK();
     return 0;
 }

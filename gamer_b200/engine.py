@@ -394,7 +394,9 @@ def forward_stack(arch: Arch, pack: Pack, input_ids, meta: BatchMeta, lut, save:
         inject = l in arch.inject
         Kf = arch.hidden + (arch.beh_dim if inject else 0)
         if sparse:
-            hp = torch.zeros(Mp, Kf, dtype=BF16, device=dev)       # padding rows of the permuted space stay zero
+            # padding rows of the permuted space must hold zeros (finite operands for the grouped GEMMs and wgrads);
+            # the norm kernel writes every mapped row, so only the < 128 padding rows per expert are cleared
+            hp = K.zero_unmapped_rows(torch.empty(Mp, Kf, dtype=BF16, device=dev), rows)
             _, rstd = K.rmsnorm_fwd(x, d["post_norm"], arch.eps, out=hp, row_map=perm,
                                     cat_table=d.get("beh_emb"), cat_idx=beh_idx if inject else None)
             gu = K.gemm_tn(hp, d["w_gu"], 2 * arch.inter, rows=Mp, n_groups=arch.n_exp, seg_off=seg)

@@ -266,6 +266,12 @@ def gather_rows(src, rows, n_rows_max, width=None, n_rows_dev=None, drop=None):
     return dst
 
 
+def zero_unmapped_rows(dst, rows):
+    """dst[r] = 0 for the rows r with rows[r] < 0 (padding rows of the permuted token space)."""
+    call("gamer_zero_unmapped_rows", ptr(dst), dst.stride(0), ptr(rows), dst.shape[0], dst.shape[1], _stream())
+    return dst
+
+
 def dropout_apply(x, drop):
     """dropout(x) with the mask of `drop` (x contiguous [R, W]); the backward of a dropout fused into a GEMM epilogue."""
     out = torch.empty_like(x)

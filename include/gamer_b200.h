@@ -140,6 +140,9 @@ int gamer_gate_residual_bwd(const void* dout, const void* y, const void* g, long
 /* dst[r] = dropout_mask[rows[r]] * src[rows[r]]  (0 where rows[r] < 0) */
 int gamer_gather_rows(const void* src, long long ld_src, const int* rows, const int* n_rows_dev, long long n_rows_max,
                       void* dst, long long ld_dst, int W, const gamer_dropout_t* drop, gamer_stream_t stream);
+/* dst[r, 0..W) = 0 where rows[r] < 0: the padding rows of the expert-permuted token space (the rows the reference never
+ * materialises: Qwen3Moe/FFN.py:64-68 indexes each expert's tokens), so that the grouped GEMMs see finite operands there */
+int gamer_zero_unmapped_rows(void* dst, long long ld_dst, const int* rows, long long n_rows, int W, gamer_stream_t stream);
 /* out = dropout(in) with the mask of `drop` (backward of a residual-branch dropout fused into a GEMM epilogue) */
 int gamer_dropout_apply(const void* in, void* out, long long R, int W, const gamer_dropout_t* drop,
                         gamer_stream_t stream);
