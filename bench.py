@@ -333,6 +333,26 @@ def eval_leg(args, dev, world, rank, barrier):
     return obj
 
 
+def _traffic_note(r):
+    """DRAM traffic a little BELOW the algorithmic bytes is an L2 effect, not an accounting error: say so in the line."""
+    if r.get("traffic") and r.get("algorithmic_bytes_per_launch") and r["traffic"] < r["algorithmic_bytes_per_launch"]:
+        r["traffic_note"] = ("DRAM traffic below the algorithmic bytes: part of the activation operand is still resident in "
+                             "the 126 MB L2 from the kernel that produced it (dram__bytes counts misses only)")
+
+
+def _both_sides(r, top, peaks):
+    """A kernel with FLOPs AND bytes gets the other side of its roofline too: algorithmic GB/s against the HBM peak, its
+    arithmetic intensity and the ridge.  Below the ridge the HBM side is the one that binds (the K = 256 projections)."""
+    if top["flops"] > 0 and top["bytes"] > 0 and top["ms"] > 0:
+        tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        gbs = top["bytes"] / (top["ms"] / 1e3) / 1e9
+        r["hbm_side"] = {"achieved_gbs": gbs, "frac": gbs / hbm_peak, "flop_per_byte": top["flops"] / top["bytes"],
+                         "ridge_flop_per_byte": tens_peak * 1e12 / (hbm_peak * 1e9),
+                         "binding": "hbm" if top["flops"] / top["bytes"] < tens_peak * 1e12 / (hbm_peak * 1e9) else "tensor"}
+    return r
+
+
 def _roofline_of(name, top, step_ms, peaks):
     tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -340,9 +360,10 @@ def _roofline_of(name, top, step_ms, peaks):
         ach, peak, unit, bound = top["flops"] / (top["ms"] / 1e3) / 1e12, tens_peak, "TFLOP/s", "tensor"
     else:
         ach, peak, unit, bound = top["bytes"] / (top["ms"] / 1e3) / 1e9, hbm_peak, "GB/s", "hbm"
-    return {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
-            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-            "share_of_step": top["ms"] / step_ms, "avg_launch_ms": top["ms"] / max(1, top["calls"])}
+    return _both_sides(
+        {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+         "share_of_step": top["ms"] / step_ms, "avg_launch_ms": top["ms"] / max(1, top["calls"])}, top, peaks)
 
 
 def _breakdown_of(summ, peaks):
@@ -734,9 +755,11 @@ def main():
                 roof["traffic_unit"] = "bytes/launch"
                 roof["algorithmic_bytes_per_launch"] = top["bytes"] / max(1, top["calls"])
                 roof["traffic_source"] = tr["source"]
+                _traffic_note(roof)
         except Exception:
             pass
         roof["peak_source"] = peak_src
+        _both_sides(roof, top, peaks)
         roof["share_of_step"] = top["ms"] / step_ms
         roof["avg_launch_ms"] = top["ms"] / max(1, top["calls"])
         roof["note"] = ("launch duration: CUDA events around every launch of this entry point during one eager step of "
@@ -772,6 +795,7 @@ def main():
                     r["traffic"] = tr["bytes_per_launch"]
                     r["algorithmic_bytes_per_launch"] = breakdown_all[n]["bytes"] / max(1, breakdown_all[n]["calls"])
                     r["traffic_source"] = tr["source"]
+                    _traffic_note(r)
                 rooflines[n] = r
         line = {"metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
