@@ -313,12 +313,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             } else {
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
                 const int row = row0 + trow;
                 long long orow = -1;
                 if (row < row_end) orow = (p.row_map != nullptr) ? (long long)p.row_map[row] : (long long)row;
-#pragma unroll 1
+                // The residual row does not depend on the accumulator: with a 128-wide tile its 256 bytes per thread are
+                // fetched BEFORE the wait for the MMAs, so the scattered-row epilogue (expert down-projection) no longer
+                // pays one memory round trip per 32-column chunk.
+                constexpr bool PRE = (BN == 128) && !OUT_F32;
+                bf16x8 pre[PRE ? 16 : 1];
+                const bool pre_ok = PRE && p.resid != nullptr && orow >= 0 && (n_blk + 1) * BN <= p.N;
+                if constexpr (PRE) {
+                    if (pre_ok) {
+                        const bf16* rp = p.resid + orow * p.ldr + n_blk * BN;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) pre[q] = *reinterpret_cast<const bf16x8*>(rp + 8 * q);
+                    }
+                }
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
                 for (int c = 0; c < BN; c += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c, r);
@@ -335,7 +348,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const bool full = (col0 + 32 <= p.N);
                         if (p.resid != nullptr) {
                             const bf16* rp = p.resid + orow * p.ldr + col0;
-                            if (full) {
+                            if (PRE && pre_ok) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    float f[8];
+                                    bf16x8_to_float(pre[PRE ? (c / 32) * 4 + q : 0], f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[8 * q + i] += f[i];
+                                }
+                            } else if (full) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     bf16x8 rv = *reinterpret_cast<const bf16x8*>(rp + 8 * q);
