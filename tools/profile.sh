@@ -23,3 +23,13 @@ timeout 300 $NCU -k regex:'attn_decode_kernel|beam_step_kernel' -s 26 -c 4 -o $O
 timeout 300 $NCU -k regex:'embed_route_kernel|emb_reduce_kernel' -s 2 -c 2 -o $OUT/prof_${TAG}_embed \
   python tools/embed_bench.py --iters 3 > $OUT/prof_${TAG}_embed.stdout 2>&1
 ls -la $OUT | tail -12
+# DRAM traffic of every GEMM launch of one eager headline step (bench.py's roofline.traffic for the GEMM entry points)
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+  -k regex:'gemm_tn_kernel|wgrad_kernel' -s 168 -c 168 --csv --log-file $OUT/gemm_traffic_$TAG.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-eval --no-cuda-graphs > $OUT/gemm_traffic_$TAG.stdout 2>&1
+# the memory-bound backward kernels inside the step
+timeout 600 $NCU -k regex:'qk_norm_rope_bwd_kernel|rmsnorm_bwd_kernel|swiglu_bwd_kernel|qk_norm_rope_fwd_kernel' -s 30 -c 10 \
+  -o $OUT/prof_${TAG}_elem python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-eval --no-cuda-graphs \
+  > $OUT/prof_${TAG}_elem.stdout 2>&1
+ls -la $OUT | tail -12
+
