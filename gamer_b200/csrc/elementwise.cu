@@ -252,14 +252,17 @@ inline int grid_for(long long total, int threads) {
 }
 
 // dst[r, 0..W) = 0 for every row r with rows[r] < 0 (the padding rows of the expert-permuted token space): a warp
-// per row, 16 bytes per lane; mapped rows are only looked at.
+// looks at 32 map entries per iteration (one coalesced load) and clears the unmapped ones, 16 bytes per lane.
 __global__ void zero_unmapped_rows_kernel(bf16* __restrict__ dst, long long ld, const int* __restrict__ rows,
                                           long long n_rows, int W) {
     const int lane = threadIdx.x & 31;
     const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (long long r = w0; r < n_rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
-        if (rows[r] >= 0) continue;
-        for (int c = lane * 8; c < W; c += 256) *reinterpret_cast<uint4*>(dst + r * ld + c) = make_uint4(0, 0, 0, 0);
+    for (long long r0 = w0 * 32; r0 < n_rows; r0 += (long long)gridDim.x * (blockDim.x >> 5) * 32) {
+        const bool unmapped = (r0 + lane < n_rows) && rows[r0 + lane] < 0;
+        for (unsigned m = __ballot_sync(0xffffffffu, unmapped); m; m &= m - 1) {
+            const long long r = r0 + (__ffs(m) - 1);
+            for (int c = lane * 8; c < W; c += 256) *reinterpret_cast<uint4*>(dst + r * ld + c) = make_uint4(0, 0, 0, 0);
+        }
     }
 }
 
@@ -327,7 +330,7 @@ extern "C" int gamer_zero_unmapped_rows(void* dst, long long ld_dst, const int* 
                                         cudaStream_t stream) {
     GAMER_REQUIRE(W % 8 == 0 && ld_dst % 8 == 0, "width and row stride must be multiples of 8");
     if (n_rows == 0) return 0;
-    const long long blocks = (n_rows + 7) / 8;
+    const long long blocks = (n_rows + 255) / 256;       // 8 warps x 32 map entries per block and iteration
     zero_unmapped_rows_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(
         reinterpret_cast<bf16*>(dst), ld_dst, rows, n_rows, W);
     GAMER_LAUNCH_CHECK();

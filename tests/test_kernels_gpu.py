@@ -492,3 +492,18 @@ def test_attention_long_history(kind):
     for name, sl in (("dq", slice(0, 384)), ("dk", slice(384, 576)), ("dv", slice(576, 768))):
         e = rel_err(dqkv[:, sl], g[:, sl])
         assert e < 2e-2, (name, e)
+
+
+def test_zero_unmapped_rows():
+    """Rows whose map entry is negative are cleared, the others are left alone (ragged row count, strided rows)."""
+    k = _k()
+    torch.manual_seed(5)
+    n, W = 1000 + 37, 320
+    buf = bf(torch.randn(n, W + 64, device=DEV))[:, :W]
+    before = buf.clone()
+    rows = torch.randint(0, 50, (n,), dtype=torch.int32, device=DEV)
+    rows[torch.rand(n, device=DEV) < 0.2] = -1
+    rows[-1] = -1
+    k.zero_unmapped_rows(buf, rows)
+    neg = rows < 0
+    assert (buf[neg] == 0).all() and torch.equal(buf[~neg], before[~neg])
